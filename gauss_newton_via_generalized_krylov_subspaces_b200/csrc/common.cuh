@@ -1,0 +1,121 @@
+// common.cuh -- shared device helpers and the context object of the gnk_b200 library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "gnk_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct gnk_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // cross-CTA reduction scratch: partial sums and self-resetting tickets (one per call site)
+  double* d_partials = nullptr;   // GNK_PARTIALS doubles
+  unsigned int* d_tickets = nullptr;  // GNK_TICKETS uints, zero-initialised
+  // TSQR R-factor ping/pong buffers
+  double* d_rbuf[2] = {nullptr, nullptr};
+  size_t rbuf_bytes = 0;
+  // communicator (comm.cu)
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  double* d_gather = nullptr;     // all-gather staging
+  size_t gather_bytes = 0;
+  // pinned host scalars for the C-side loops (cgls)
+  double* h_pinned = nullptr;
+};
+
+constexpr int GNK_PARTIALS = 1 << 18;  // doubles (2 MiB)
+constexpr int GNK_TICKETS = 64;
+
+enum TicketSlot { TK_RESID = 0, TK_STATS = 1, TK_DOTS = 2, TK_UPDATE = 3, TK_DOT1 = 4, TK_CG = 5 };
+
+void gnk_set_error(const std::string& s);
+int gnk_fail(const char* what, cudaError_t e, const char* file, int line);
+
+#define GNK_CUDA(expr)                                                    \
+  do {                                                                    \
+    cudaError_t e__ = (expr);                                             \
+    if (e__ != cudaSuccess) return gnk_fail(#expr, e__, __FILE__, __LINE__); \
+  } while (0)
+
+#define GNK_LAUNCH_CHECK(ctx)                                             \
+  do {                                                                    \
+    (ctx)->launches++;                                                    \
+    cudaError_t e__ = cudaGetLastError();                                 \
+    if (e__ != cudaSuccess) return gnk_fail("kernel launch", e__, __FILE__, __LINE__); \
+  } while (0)
+
+#define GNK_REQUIRE(cond, msg)                                            \
+  do {                                                                    \
+    if (!(cond)) {                                                        \
+      gnk_set_error(std::string(msg) + " (" #cond ")");                   \
+      return -2;                                                          \
+    }                                                                     \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum with a fixed reduction tree (deterministic).  `sh` needs 32 doubles.  The result is
+// valid in every thread of warp 0.  Ends with the shared buffer free for reuse after a __syncthreads.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double r = (w == 0 && lane < nw) ? sh[lane] : 0.0;
+  if (w == 0) r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double r = (w == 0 && lane < nw) ? sh[lane] : 0.0;  // inputs are |.| >= 0
+  if (w == 0) r = warp_max(r);
+  return r;
+}
+
+// "last CTA finishes" pattern.  Thread 0 of every CTA has published its partial(s) to global memory
+// before calling; returns true in ALL threads of the CTA that arrives last.  The ticket wraps back
+// to 0, so the same slot serves the next launch without a memset.
+__device__ __forceinline__ bool grid_arrive_last(unsigned int* ticket) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicInc(ticket, gridDim.x * gridDim.y * gridDim.z - 1);
+    s_last = (t == gridDim.x * gridDim.y * gridDim.z - 1);
+    __threadfence();
+  }
+  __syncthreads();
+  return s_last != 0;
+}
+
+__device__ __forceinline__ unsigned int linear_block_id() {
+  return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+}
+__device__ __forceinline__ unsigned int total_blocks() { return gridDim.x * gridDim.y * gridDim.z; }
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,372 @@
+// vector_ops.cu -- basis-sized streaming kernels of the GNK hot path (all HBM-bound, fp64):
+//   combine     x = V_k (c + s d)                 krylow.py:41-42, armijo_goldstein.py:56
+//   norm_stats  sum x^2, max|x|                   krylow.py:31,36,66,71
+//   normalize   x / ||x||                         krylow.py:37,71
+//   cgs_dots    h = V_k^T w                       krylow.py:64 (inner product half)
+//   cgs_update  w -= V_k h  (+ stats of new w)    krylow.py:64 (update half) + :66,:71
+//   axpby, dot                                    gauss_newton.py:123-129
+// Every thread moves 128-bit (double2) words, columns are walked with independent loads in flight,
+// grids are sized in multiples of the SM count, cross-CTA reductions use a fixed-order
+// "last CTA finishes" tree so results are run-to-run deterministic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 ld2_stream(const double* p) {
+  return __ldcs(reinterpret_cast<const double2*>(p));
+}
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) combine_kernel(const double* __restrict__ V, int64_t ld, int64_t len,
+                                                       int k, const double* __restrict__ c,
+                                                       const double* __restrict__ d, double s,
+                                                       double* __restrict__ x) {
+  __shared__ double coef[GNK_MAX_BASIS];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) coef[j] = d ? (c[j] + s * d[j]) : c[j];
+  __syncthreads();
+  const int64_t nv = len >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const double* p = V + 2 * i;
+    double2 acc = make_double2(0.0, 0.0);
+    int j = 0;
+    for (; j + 8 <= k; j += 8) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ld2_stream(p + (int64_t)(j + u) * ld);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x = fma(v[u].x, coef[j + u], acc.x);
+        acc.y = fma(v[u].y, coef[j + u], acc.y);
+      }
+    }
+    for (; j < k; ++j) {
+      double2 v = ld2_stream(p + (int64_t)j * ld);
+      acc.x = fma(v.x, coef[j], acc.x);
+      acc.y = fma(v.y, coef[j], acc.y);
+    }
+    st2(x + 2 * i, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sum of squares + max abs over x[0..n); partials[b*2 + {0,1}]
+__global__ void __launch_bounds__(TPB) stats_kernel(const double* __restrict__ x, int64_t n,
+                                                     double* __restrict__ partials, unsigned int* ticket,
+                                                     double* __restrict__ out) {
+  __shared__ double sh[32];
+  const int64_t nv = n >> 1;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double ss = 0.0, mx = 0.0;
+  for (int64_t i = gt; i < nv; i += stride) {
+    double2 v = ld2(x + 2 * i);
+    ss = fma(v.x, v.x, ss);
+    ss = fma(v.y, v.y, ss);
+    mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+  }
+  if ((n & 1) && gt == 0) {
+    double v = x[n - 1];
+    ss = fma(v, v, ss);
+    mx = fmax(mx, fabs(v));
+  }
+  ss = block_sum(ss, sh);
+  mx = block_max(mx, sh);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = ss;
+    partials[2 * blockIdx.x + 1] = mx;
+  }
+  if (grid_arrive_last(ticket)) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+      a += __ldcg(partials + 2 * i);
+      b = fmax(b, __ldcg(partials + 2 * i + 1));
+    }
+    a = block_sum(a, sh);
+    b = block_max(b, sh);
+    if (threadIdx.x == 0) {
+      out[0] = a;
+      out[1] = b;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TPB) normalize_kernel(const double* __restrict__ x, int64_t len,
+                                                         const double* __restrict__ stats, double atol,
+                                                         double* __restrict__ out, int32_t* flag) {
+  const double ss = stats[0], mx = stats[1];
+  const bool bad = (mx <= atol);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *flag = bad ? 1 : 0;
+  if (bad) return;
+  const double nrm = sqrt(ss);
+  const int64_t nv = len >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    double2 v = ld2(x + 2 * i);
+    v.x = v.x / nrm;
+    v.y = v.y / nrm;
+    st2(out + 2 * i, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// h[j] = sum_i V[j*ld + i] * w[i], i in [0, n) (pointers already offset to the owned part)
+constexpr int JB = 16;
+__global__ void __launch_bounds__(TPB) dots_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
+                                                    const double* __restrict__ w, double* __restrict__ partials,
+                                                    unsigned int* ticket, double* __restrict__ h) {
+  __shared__ double sh[32];
+  const int64_t nv = n >> 1;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int jb = 0; jb < k; jb += JB) {
+    double acc[JB];
+#pragma unroll
+    for (int u = 0; u < JB; ++u) acc[u] = 0.0;
+    const int nj = min(JB, k - jb);
+    const double* Vb = V + (int64_t)jb * ld;
+    if (nj == JB) {
+      for (int64_t i = gt; i < nv; i += stride) {
+        const double2 wv = ld2(w + 2 * i);
+        double2 v[JB];
+#pragma unroll
+        for (int u = 0; u < JB; ++u) v[u] = ld2_stream(Vb + (int64_t)u * ld + 2 * i);
+#pragma unroll
+        for (int u = 0; u < JB; ++u) acc[u] = fma(v[u].y, wv.y, fma(v[u].x, wv.x, acc[u]));
+      }
+    } else {
+      for (int64_t i = gt; i < nv; i += stride) {
+        const double2 wv = ld2(w + 2 * i);
+#pragma unroll
+        for (int u = 0; u < JB; ++u)
+          if (u < nj) {
+            double2 v = ld2_stream(Vb + (int64_t)u * ld + 2 * i);
+            acc[u] = fma(v.y, wv.y, fma(v.x, wv.x, acc[u]));
+          }
+      }
+    }
+    if ((n & 1) && gt == 0) {
+      const double wv = w[n - 1];
+#pragma unroll
+      for (int u = 0; u < JB; ++u)
+        if (u < nj) acc[u] = fma(Vb[(int64_t)u * ld + n - 1], wv, acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < JB; ++u) {
+      if (u < nj) {
+        double r = block_sum(acc[u], sh);
+        if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * GNK_MAX_BASIS + jb + u] = r;
+      }
+    }
+  }
+  if (grid_arrive_last(ticket)) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = wid; j < k; j += nw) {
+      double a = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) a += __ldcg(partials + (int64_t)b * GNK_MAX_BASIS + j);
+      a = warp_sum(a);
+      if (lane == 0) h[j] = a;
+    }
+  }
+}
+
+// w[i] -= sum_j V[j*ld+i] h[j]; stats of the new w
+__global__ void __launch_bounds__(TPB) update_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
+                                                      const double* __restrict__ h, double* __restrict__ w,
+                                                      double* __restrict__ partials, unsigned int* ticket,
+                                                      double* __restrict__ stats) {
+  __shared__ double coef[GNK_MAX_BASIS];
+  __shared__ double sh[32];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) coef[j] = h[j];
+  __syncthreads();
+  const int64_t nv = n >> 1;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double ss = 0.0, mx = 0.0;
+  for (int64_t i = gt; i < nv; i += stride) {
+    const double* p = V + 2 * i;
+    double2 acc = make_double2(0.0, 0.0);
+    int j = 0;
+    for (; j + 8 <= k; j += 8) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ld2_stream(p + (int64_t)(j + u) * ld);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x = fma(v[u].x, coef[j + u], acc.x);
+        acc.y = fma(v[u].y, coef[j + u], acc.y);
+      }
+    }
+    for (; j < k; ++j) {
+      double2 v = ld2_stream(p + (int64_t)j * ld);
+      acc.x = fma(v.x, coef[j], acc.x);
+      acc.y = fma(v.y, coef[j], acc.y);
+    }
+    double2 wv = ld2(w + 2 * i);
+    wv.x -= acc.x;
+    wv.y -= acc.y;
+    st2(w + 2 * i, wv);
+    ss = fma(wv.x, wv.x, ss);
+    ss = fma(wv.y, wv.y, ss);
+    mx = fmax(mx, fmax(fabs(wv.x), fabs(wv.y)));
+  }
+  if ((n & 1) && gt == 0) {
+    double acc = 0.0;
+    for (int j = 0; j < k; ++j) acc = fma(V[(int64_t)j * ld + n - 1], coef[j], acc);
+    double wv = w[n - 1] - acc;
+    w[n - 1] = wv;
+    ss = fma(wv, wv, ss);
+    mx = fmax(mx, fabs(wv));
+  }
+  if (stats == nullptr) return;
+  ss = block_sum(ss, sh);
+  mx = block_max(mx, sh);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = ss;
+    partials[2 * blockIdx.x + 1] = mx;
+  }
+  if (grid_arrive_last(ticket)) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+      a += __ldcg(partials + 2 * i);
+      b = fmax(b, __ldcg(partials + 2 * i + 1));
+    }
+    a = block_sum(a, sh);
+    b = block_max(b, sh);
+    if (threadIdx.x == 0) {
+      stats[0] = a;
+      stats[1] = b;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) axpby_kernel(int64_t n, double a, const double* x, double b,
+                                                     const double* y, double* out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double r = 0.0;
+    if (a != 0.0) r = a * x[i];
+    if (b != 0.0) r = fma(b, y[i], r);
+    out[i] = r;
+  }
+}
+
+__global__ void __launch_bounds__(TPB) dot_kernel(int64_t n, const double* __restrict__ x,
+                                                   const double* __restrict__ y, double* __restrict__ partials,
+                                                   unsigned int* ticket, double* __restrict__ out) {
+  __shared__ double sh[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s = fma(x[i], y[i], s);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  if (grid_arrive_last(ticket)) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) a += __ldcg(partials + i);
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) out[0] = a;
+  }
+}
+
+inline int stream_grid(const gnk_ctx* ctx, int64_t items, int per_sm) {
+  int64_t g = ceil_div(items, TPB);
+  int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+// Region offsets inside ctx->d_partials so that kernels running back to back on one stream never
+// share scratch with a still-running predecessor's "last CTA" phase (stream order already
+// serialises them; the split is belt and braces for multi-stream callers).
+static constexpr int64_t PART_STATS = 0;
+static constexpr int64_t PART_DOTS = 8192;
+static constexpr int64_t PART_UPDATE = PART_DOTS + 1184 * GNK_MAX_BASIS;
+static constexpr int64_t PART_DOT1 = PART_UPDATE + 8192;
+
+extern "C" {
+
+int gnk_combine(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_c,
+                const double* d_d, double s, double* d_x, void* stream) {
+  GNK_REQUIRE(ctx && lay && d_V && d_c && d_x, "gnk_combine: null argument");
+  GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_combine: k out of range");
+  GNK_REQUIRE((lay->ld & 1) == 0, "gnk_combine: ld must be even");
+  int grid = stream_grid(ctx, lay->ld / 2, 8);
+  combine_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V, lay->ld, lay->ld, k, d_c, d_d, s, d_x);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gnk_norm_stats(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, double* d_stats, void* stream) {
+  GNK_REQUIRE(ctx && lay && d_x && d_stats, "gnk_norm_stats: null argument");
+  GNK_REQUIRE((lay->off & 1) == 0, "gnk_norm_stats: off must be even");
+  int grid = stream_grid(ctx, lay->n_own / 2, 4);
+  stats_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_x + lay->off, lay->n_own, ctx->d_partials + PART_STATS,
+                                                       ctx->d_tickets + TK_STATS, d_stats);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gnk_normalize(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, const double* d_stats, double atol,
+                  double* d_out, int32_t* d_flag, void* stream) {
+  GNK_REQUIRE(ctx && lay && d_x && d_stats && d_out && d_flag, "gnk_normalize: null argument");
+  GNK_REQUIRE((lay->ld & 1) == 0, "gnk_normalize: ld must be even");
+  int grid = stream_grid(ctx, lay->ld / 2, 8);
+  normalize_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_x, lay->ld, d_stats, atol, d_out, d_flag);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_w, double* d_h,
+                 void* stream) {
+  GNK_REQUIRE(ctx && lay && d_V && d_w && d_h, "gnk_cgs_dots: null argument");
+  GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_dots: k out of range");
+  GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_dots: off/ld must be even");
+  int grid = stream_grid(ctx, lay->n_own / 2, 4);
+  dots_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V + lay->off, lay->ld, lay->n_own, k, d_w + lay->off,
+                                                      ctx->d_partials + PART_DOTS, ctx->d_tickets + TK_DOTS, d_h);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_h, double* d_w,
+                   double* d_stats, void* stream) {
+  GNK_REQUIRE(ctx && lay && d_V && d_w && d_h, "gnk_cgs_update: null argument");
+  GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_update: k out of range");
+  GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_update: off/ld must be even");
+  int grid = stream_grid(ctx, lay->n_own / 2, 8);
+  update_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V + lay->off, lay->ld, lay->n_own, k, d_h,
+                                                        d_w + lay->off, ctx->d_partials + PART_UPDATE,
+                                                        ctx->d_tickets + TK_UPDATE, d_stats);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gnk_axpby(gnk_ctx* ctx, int64_t n, double a, const double* d_x, double b, const double* d_y, double* d_out,
+              void* stream) {
+  GNK_REQUIRE(ctx && d_out && n >= 0, "gnk_axpby: bad argument");
+  GNK_REQUIRE((a == 0.0 || d_x) && (b == 0.0 || d_y), "gnk_axpby: null operand with non-zero weight");
+  if (n == 0) return 0;
+  int grid = stream_grid(ctx, n, 8);
+  axpby_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(n, a, d_x, b, d_y, d_out);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gnk_dot(gnk_ctx* ctx, int64_t n, const double* d_x, const double* d_y, double* d_out, void* stream) {
+  GNK_REQUIRE(ctx && d_x && d_y && d_out && n >= 0, "gnk_dot: bad argument");
+  int grid = stream_grid(ctx, n, 4);
+  dot_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(n, d_x, d_y, ctx->d_partials + PART_DOT1,
+                                                     ctx->d_tickets + TK_DOT1, d_out);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (needs /root/reference,
+which does not exist on the GPU box); the fixtures it writes are committed.
+
+    python oracle/gen_golden.py small          # all n <= 1e4 configs (~1 min)
+    python oracle/gen_golden.py g1025          # Bratu 1024^2 (~5 min)
+    python oracle/gen_golden.py g4097          # Bratu 4096^2, 30 iterations (~10 min, 25 GB)
+
+Per solver run a fixture stores: the RegressionResult fields, and per callback
+|x|_2, error(x), loss 0.5|res(x)|^2, nfev, cg_iter and x sampled at fixed indices
+(``sample_idx``); the final x in full when n <= 1e4.
+"""
+import contextlib
+import io
+import os
+import sys
+import time
+
+import numpy as np
+
+REF = "/root/reference"
+sys.path.insert(0, REF)
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+from armijo_goldstein import StepLengthConvergenceError, armijo_goldstein  # noqa: E402
+from bratu_pde_problem import BratuPdeProblem  # noqa: E402
+from gauss_newton import gauss_newton  # noqa: E402
+from gauss_newton_krylow import gauss_newton_krylow  # noqa: E402
+import rosenbrock_problem  # noqa: E402
+
+
+def sample_idx(n, count=64):
+    return np.unique(np.linspace(0, n - 1, min(n, count)).astype(np.int64))
+
+
+def run(method, res, x0, jac, error, args=(), loss_every=1, **kw):
+    idx = sample_idx(x0.shape[0])
+    rec = dict(xnorm=[], err=[], loss=[], nfev=[], cg_iter=[], xs=[])
+
+    def cb(x, nfev, cg_iter):
+        rec["xnorm"].append(np.linalg.norm(x))
+        rec["err"].append(error(x) if error is not None else np.nan)
+        if loss_every and (len(rec["xnorm"]) % loss_every == 0):
+            rec["loss"].append(0.5 * np.sum(res(x, *args) ** 2))
+        else:
+            rec["loss"].append(np.nan)
+        rec["nfev"].append(-1 if nfev is None else nfev)
+        rec["cg_iter"].append(-1 if cg_iter is None else cg_iter)
+        rec["xs"].append(np.array(x[idx], copy=True))
+
+    buf = io.StringIO()
+    t0 = time.perf_counter()
+    raised = ""
+    out = None
+    with contextlib.redirect_stdout(buf):
+        try:
+            out = method(res, x0.copy(), jac, args=args, callback=cb, **kw)
+        except StepLengthConvergenceError as e:
+            raised = "StepLengthConvergenceError"
+    wall = time.perf_counter() - t0
+    d = dict(
+        sample_idx=idx,
+        xnorm=np.array(rec["xnorm"]), err=np.array(rec["err"]), loss=np.array(rec["loss"]),
+        nfev_cb=np.array(rec["nfev"]), cg_iter=np.array(rec["cg_iter"]),
+        xs=np.array(rec["xs"]).reshape(len(rec["xs"]), idx.shape[0]),
+        raised=np.array(raised), stdout=np.array(buf.getvalue()), wall_s=np.array(wall),
+    )
+    if out is not None:
+        d.update(success=np.array(out.success), nit=np.array(out.nit), nfev=np.array(out.nrev),
+                 njev=np.array(out.njev), x_sample=np.array(out.x[idx]), x_norm_final=np.array(np.linalg.norm(out.x)))
+        if x0.shape[0] <= 10000:
+            d["x_final"] = np.array(out.x)
+    return d
+
+
+def save(name, runs, **extra):
+    flat = dict(extra)
+    for rname, d in runs.items():
+        for k, v in d.items():
+            flat[f"{rname}/{k}"] = v
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **flat)
+    for rname, d in runs.items():
+        print(f"{name}:{rname}: nit={d.get('nit')} nfev={d.get('nfev')} success={d.get('success')} "
+              f"raised={d['raised']} callbacks={len(d['xnorm'])} err_last={d['err'][-1] if len(d['err']) else None} "
+              f"wall={float(d['wall_s']):.1f}s", flush=True)
+
+
+def bratu_setup(G, alpha, lam, h=None, linear_start=False):
+    pb = BratuPdeProblem(G, alpha, lam, grid_resolution=h)
+    y = pb.pde_operator(pb.u_true)
+    res, jac, err = pb.make_res(y), pb.make_jac(), pb.make_error()
+    if linear_start:
+        u0 = -1 * jac(np.zeros((G - 1) ** 2)).T @ y
+    else:
+        np.random.seed(42)
+        u0 = pb.u_true + 0.1 * np.random.normal(loc=0, scale=1, size=len(pb.u_true))
+    return pb, y, res, jac, err, u0
+
+
+def kernels_fixture():
+    """operator-level known answers straight from the reference's scipy path."""
+    flat = {}
+    for tag, (G, a, l, h) in dict(g11=(11, 5, 10, None), g10=(10, 5, 10, None), g26lin=(26, 5, 0, None),
+                                   g33h1=(33, 5, 10, 1.0), g101=(101, 5, 10, None)).items():
+        pb = BratuPdeProblem(G, a, l, grid_resolution=h)
+        rs = np.random.RandomState(7)
+        n = (G - 1) ** 2
+        u = 0.3 * rs.normal(size=n)
+        V = rs.normal(size=(n, 3))
+        r = rs.normal(size=n)
+        J = pb.make_jac()(u)
+        flat.update({f"{tag}/params": np.array([G, a, l, -1.0 if h is None else h]), f"{tag}/u": u, f"{tag}/V": V, f"{tag}/r": r,
+                     f"{tag}/P": pb.pde_operator(u), f"{tag}/JV": J @ V, f"{tag}/JTr": J.T @ r,
+                     f"{tag}/u_true": pb.u_true, f"{tag}/JTJdiag": (J.T @ J).diagonal()})
+    x = np.random.RandomState(3).normal(size=1000)
+    Jr = rosenbrock_problem.jac(x).tocsr()
+    flat.update({"rosen/x": x, "rosen/res": rosenbrock_problem.res(x), "rosen/indptr": Jr.indptr,
+                 "rosen/indices": Jr.indices, "rosen/data": Jr.data})
+    np.savez_compressed(os.path.join(OUT, "kernels.npz"), **flat)
+    print("kernels.npz written")
+
+
+def small():
+    kernels_fixture()
+    # --- bratu_pde_test.compare (bratu_pde_test.py:22-50)
+    pb, y, res, jac, err, u0 = bratu_setup(101, 5, 10)
+    save("bratu_g101", dict(
+        gnk_res_old=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100),
+        gnk_res_new=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100, version="res_new"),
+        gnk_jac_old_res_old=run(gauss_newton_krylow, res, u0, jac, err, max_iter=25, version="jac_old_res_old"),
+        gnk_jac_old_res_new=run(gauss_newton_krylow, res, u0, jac, err, max_iter=25, version="jac_old_res_new"),
+        gnk_restart30=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100, krylow_restart=30),
+        gnk_restart7_res_new=run(gauss_newton_krylow, res, u0, jac, err, max_iter=40, krylow_restart=7, version="res_new"),
+        gn=run(gauss_newton, res, u0, jac, err),
+        gn_precond=run(gauss_newton, res, u0, jac, err, cg_preconditioner=True),
+    ), y=y, u0=u0)
+    # --- compare_without_scaling (:76-103)
+    pb, y, res, jac, err, u0 = bratu_setup(101, 5, 10, h=1)
+    save("bratu_g101_h1", dict(
+        gnk_res_old=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100),
+        gnk_res_new=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100, version="res_new"),
+        gn=run(gauss_newton, res, u0, jac, err),
+    ), y=y, u0=u0)
+    # --- compare_linear (:193-241)
+    pb, y, res, jac, err, u0 = bratu_setup(101, 5, 0, linear_start=True)
+    save("bratu_g101_linear", dict(
+        gnk_res_old=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100),
+        gnk_res_new=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100, version="res_new"),
+        gn=run(gauss_newton, res, u0, jac, err),
+    ), y=y, u0=u0)
+    # --- compare_linear_small (:277-330)
+    pb, y, res, jac, err, u0 = bratu_setup(25, 5, 0, linear_start=True)
+    save("bratu_g25_linear", dict(
+        gnk_res_old=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100),
+        gnk_res_new=run(gauss_newton_krylow, res, u0, jac, err, max_iter=200, version="res_new"),
+        gn=run(gauss_newton, res, u0, jac, err),
+    ), y=y, u0=u0)
+    # --- odd m (m = 33), uneven splits
+    pb, y, res, jac, err, u0 = bratu_setup(34, 5, 10)
+    save("bratu_g34", dict(
+        gnk_res_old=run(gauss_newton_krylow, res, u0, jac, err, max_iter=40, krylow_restart=12),
+    ), y=y, u0=u0)
+    # --- rosenbrock_test i/ii/iii (rosenbrock_test.py:20-31,79-88,101-111)
+    rp = rosenbrock_problem
+    np.random.seed(42)
+    x0_i = rp.x_exact + 0.1 * np.random.normal(loc=0, scale=1, size=rp.parameter_count)
+    x0_ii = 2 * rp.x_exact
+    x0_iii = 2 * rp.x_exact
+    x0_iii[2] = 1.99
+    runs = {}
+    for tag, x0 in (("i", x0_i), ("ii", x0_ii), ("iii", x0_iii)):
+        runs[f"{tag}_gnk_res_old"] = run(gauss_newton_krylow, rp.res, x0, rp.jac, rp.error)
+        runs[f"{tag}_gnk_res_new"] = run(gauss_newton_krylow, rp.res, x0, rp.jac, rp.error, version="res_new")
+        runs[f"{tag}_gn"] = run(gauss_newton, rp.res, x0, rp.jac, rp.error)
+    save("rosenbrock", runs, x0_i=x0_i, x0_ii=x0_ii, x0_iii=x0_iii)
+    # --- rosenbrock_3d_test.py:20-36,74 (dense Jacobian -> lstsq path)
+    import scipy.sparse
+
+    def res2(x):
+        return 2 ** 0.5 * np.concatenate([10 * (x[1:] - x[:-1] ** 2), 1 - x[:-1]])
+
+    def jac2(x):
+        b1 = 10 * scipy.sparse.eye(1, 2, k=1) - 20 * scipy.sparse.diags(x[:-1], shape=(1, 2))
+        b2 = -scipy.sparse.eye(1, 2, k=0)
+        return 2 ** 0.5 * scipy.sparse.block_array([[b1], [b2]]).todense()
+
+    x0 = np.array([-1.0, 1.0])
+    d = run(gauss_newton, res2, x0, jac2, None)
+    save("rosenbrock_3d", dict(gn=d))
+    # --- powell_divergence_test.py:17-61,87-102,192-204
+    def pres(x, tau):
+        return np.array([x[0] + 1, tau * x[0] ** 2 + x[0] - 1])
+
+    def pjac(x, tau):
+        return np.array([[1], [2 * tau * x[0] + 1]])
+
+    def no_step_length_control(res, x, res_ev, jac_ev, args, descent_direction, *_):
+        return 1, res(x + descent_direction, *args), 1
+
+    state = dict(it=2)
+
+    def too_small_steps(res, x, res_ev, jac_ev, args, descent_direction, *_):
+        step_length = -1 / descent_direction[0] * 2 ** -state["it"]
+        state["it"] += 1
+        return step_length, res(x + step_length * descent_direction, *args), 1
+
+    x0 = np.array([1.0])
+    runs = {}
+    for tau in (-5, 5):
+        for ctl in (armijo_goldstein, too_small_steps, no_step_length_control):
+            if tau == 5 and ctl is too_small_steps:
+                continue
+            state["it"] = 2
+            runs[f"tau{tau}_{ctl.__name__}"] = run(gauss_newton, pres, x0, pjac, None, args=(tau,), max_iter=19,
+                                                   step_length_control=ctl)
+    save("powell", runs)
+
+
+def g1025():
+    pb, y, res, jac, err, u0 = bratu_setup(1025, 5, 10)
+    save("bratu_g1025", dict(
+        gnk_restart30=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100, krylow_restart=30),
+        gnk_k30=run(gauss_newton_krylow, res, u0, jac, err, max_iter=31),
+    ), y_sample=y[sample_idx(y.shape[0])], u0_sample=u0[sample_idx(u0.shape[0])])
+
+
+def g4097():
+    pb, y, res, jac, err, u0 = bratu_setup(4097, 5, 10)
+    save("bratu_g4097", dict(
+        gnk_k30=run(gauss_newton_krylow, res, u0, jac, err, max_iter=31),
+    ), y_sample=y[sample_idx(y.shape[0])], u0_sample=u0[sample_idx(u0.shape[0])])
+
+
+if __name__ == "__main__":
+    for what in sys.argv[1:] or ["small"]:
+        dict(small=small, g1025=g1025, g4097=g4097, kernels=kernels_fixture)[what]()
