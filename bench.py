@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- GN-Krylov outer iterations/s on the Bratu problem (BASELINE.json metric).
+
+A "step" is one complete GNK solve of the north-star workload: Bratu grid_nodes=4097 (n = 4096^2 = 16.7M
+unknowns), ALPHA=5, LAMBDA=10, u0 = u_true + 0.1*N(0,1) (numpy legacy seed 42, drawn on the host), Krylov
+dimension <= 30 realised as krylow_restart=None, max_iter=31  ->  30 outer iterations, k = 1..30 (SURVEY 8c':
+every decision of this run is robust, it is the first 30 iterations of the reference's restart-30 run).
+
+  value    iterations/s with u0 and y resident in HBM and the result left in HBM
+  e2e      the same through the public API with HOST buffers: make_res(y) + gauss_newton_krylow(res, u0, jac)
+           -> host ndarray, i.e. H2D of y and u0 (pinned) and D2H of x inside the timed region
+  roofline the dominant kernel of the step: algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS.json
+  cpu_baseline   the numpy/scipy oracle (port of the reference's CPU path) on the host cores, bounded sample
+
+`--impl reference` times the reference's CPU algorithm (oracle port; /root/reference does not exist on the GPU
+box) on the host cores on the same workload, each step a bounded sample of it.
+
+Multi-GPU (torchrun, one rank per GPU): the grid rows are partitioned into slabs, scaling is strong.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gnk_outer_iterations_per_second"
+UNIT = "it/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid-nodes", type=int, default=4097)
+    ap.add_argument("--iters", type=int, default=30, help="outer iterations per step (k = 1..iters)")
+    ap.add_argument("--restart", type=int, default=None)
+    ap.add_argument("--reorth", type=int, default=1, help="Gram-Schmidt passes (1 = reference, 2 = CGS2)")
+    ap.add_argument("--cpu-sample-iters", type=int, default=2, help="outer iterations of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(a):
+    return dict(workload=f"bratu_{a.grid_nodes - 1}x{a.grid_nodes - 1}_gnk_k{a.iters}", grid_nodes=a.grid_nodes,
+                unknowns=(a.grid_nodes - 1) ** 2, ALPHA=5, LAMBDA=10, krylow_restart=a.restart, max_iter=a.iters + 1,
+                version="res_old", tol=1e-8, cgs_passes=a.reorth,
+                l2="inputs (basis 0.13-4 GB) exceed the 126 MB L2; no explicit flush")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path, all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(a, iters):
+    from oracle import gnk_oracle as orc
+    o = orc.BratuOracle(a.grid_nodes, 5, 10)
+    y = o.operator(o.u_true)
+    u0 = o.start_vector(seed=42)
+    res, jac = o.make_res(y), o.make_jac()
+    t0 = time.perf_counter()
+    out = orc.gnk(res, u0, jac, restart=a.restart, max_iter=iters + 1, callback=lambda **kw: None)
+    dt = time.perf_counter() - t0
+    return out["nit"], dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    times, its = [], 0
+    for s in range(a.warmup + a.steps):
+        nit, dt = cpu_sample(a, a.cpu_sample_iters)
+        if s >= a.warmup:
+            times.append(dt)
+            its += nit
+    total = sum(times)
+    val = its / total
+    sample = (f"first {a.cpu_sample_iters} outer iterations (k=1..{a.cpu_sample_iters}) of the same workload per step; "
+              "per-iteration CPU cost grows with k (SURVEY 6: 6.9 s at k=1 -> 29 s at k=30), so this flatters the CPU")
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=1e3 * total / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference", config=workload(a),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # clocks are diagnostics; never fail the bench on NVML
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.max_sm,
+                    reasons=sorted(self.reasons))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import gauss_newton_via_generalized_krylov_subspaces_b200 as g
+
+    rt = g.get_runtime()
+    G = a.grid_nodes
+    n = (G - 1) ** 2
+    pb = g.BratuPdeProblem(G, 5, 10)
+    u_true = pb.u_true
+    y = pb.pde_operator(u_true)
+    u0 = u_true + 0.1 * np.random.RandomState(42).normal(loc=0, scale=1, size=n)
+    # pinned host copies for the e2e leg (the user's buffers)
+    y_pin = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    u0_pin = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    y_pin.numpy()[:] = y
+    u0_pin.numpy()[:] = u0
+    kw = dict(krylow_restart=a.restart, max_iter=a.iters + 1, callback=lambda **k: None, reorth_passes=a.reorth)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg -------------------------------------------------------------------
+    res = pb.make_res(y)
+    res.y_col  # upload y once
+    jac = pb.make_jac()
+    x0_dev = pb.dev.resident(u0)
+
+    def step_resident():
+        return g.gauss_newton_krylow(res, x0_dev, jac, x_on_device=True, **kw)
+
+    for _ in range(a.warmup):
+        out = step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = rt.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    its = 0
+    for _ in range(a.steps):
+        out = step_resident()
+        its += out.nit
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = rt.launches() - l0
+    tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    value = its / (ms * 1e-3)
+    nit, nfev, success = out.nit, out.nrev, bool(out.success)
+
+    # ---- per-kernel roofline pass (events around every kernel; not part of the headline timing) ---
+    rt.begin_profile()
+    step_resident()
+    prof = rt.end_profile()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    kernels = {}
+    for name, p in prof.items():
+        gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
+        kernels[name] = dict(launches=p["launches"], ms=round(p["ms"], 3), achieved_gbs=round(gbs, 1),
+                             frac=round(gbs / peak, 3), bytes_per_launch=p["bytes"] / max(p["launches"], 1))
+    top = max(prof, key=lambda k_: prof[k_]["ms"]) if prof else None
+    roofline = None
+    if top:
+        roofline = dict(bound="hbm", kernel=top, achieved=kernels[top]["achieved_gbs"], peak=peak, unit="GB/s",
+                        frac=kernels[top]["frac"], traffic=None, peak_source=peak_src,
+                        share_of_step=round(prof[top]["ms"] / sum(p["ms"] for p in prof.values()), 3))
+
+    # ---- end-to-end leg: host buffers in, host ndarray out ----------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        def step_e2e():
+            r = pb.make_res(y_pin.numpy())
+            j = pb.make_jac()
+            o = g.gauss_newton_krylow(r, u0_pin.numpy(), j, **kw)
+            return o
+
+        for _ in range(max(1, a.warmup - 1)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        its_e = 0
+        for _ in range(a.steps):
+            o = step_e2e()
+            its_e += o.nit
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        f = pb.dev.fields
+        h2d = 2 * 8 * (f["n_own"] if world == 1 else (f["rows"] + 4) * f["m"])
+        e2e = dict(value=its_e / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(8 * n),
+                   ms_per_step=1e3 * dt / a.steps, final_loss=float(0.5 * np.sum(pb.make_res(y)(o.x) ** 2)))
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        nit_c, dt_c = cpu_sample(a, a.cpu_sample_iters)
+        cpu = dict(value=nit_c / dt_c, unit=UNIT, cores=os.cpu_count(), kind="port",
+                   sample=f"first {a.cpu_sample_iters} outer iterations (k=1..{a.cpu_sample_iters}) of the same "
+                          f"workload, {dt_c:.1f} s; CPU cost per iteration grows with k, so this flatters the CPU")
+
+    if rank == 0:
+        cfg = workload(a)
+        cfg["parallelism"] = f"row_slabs_x{world}"
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=ms / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                    data="synthetic", config=cfg, clocks=sampler.summary(), e2e=e2e, gpu_launches=int(launches),
+                    roofline=roofline, kernels=kernels, cpu_baseline=cpu,
+                    result=dict(nit=nit, nfev=nfev, success=success))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

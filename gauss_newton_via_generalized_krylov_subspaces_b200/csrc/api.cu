@@ -1,0 +1,64 @@
+// api.cu -- context lifecycle and error reporting of the gnk_b200 C ABI.
+#include "common.cuh"
+
+void gnk_comm_teardown(gnk_ctx* ctx);
+
+namespace {
+thread_local std::string g_err;
+}
+
+void gnk_set_error(const std::string& s) { g_err = s; }
+
+int gnk_fail(const char* what, cudaError_t e, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  g_err = buf;
+  return -1;
+}
+
+extern "C" {
+
+int gnk_abi_version(void) { return GNK_B200_ABI_VERSION; }
+
+const char* gnk_last_error(void) { return g_err.c_str(); }
+
+int gnk_create(gnk_ctx** out, int device) {
+  GNK_REQUIRE(out, "gnk_create: null argument");
+  *out = nullptr;
+  int count = 0;
+  GNK_CUDA(cudaGetDeviceCount(&count));
+  GNK_REQUIRE(device >= 0 && device < count, "gnk_create: no such CUDA device");
+  GNK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GNK_CUDA(cudaGetDeviceProperties(&prop, device));
+  gnk_ctx* ctx = new gnk_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  GNK_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * GNK_PARTIALS));
+  GNK_CUDA(cudaMemset(ctx->d_partials, 0, sizeof(double) * GNK_PARTIALS));
+  GNK_CUDA(cudaMalloc(&ctx->d_tickets, sizeof(unsigned int) * GNK_TICKETS));
+  GNK_CUDA(cudaMemset(ctx->d_tickets, 0, sizeof(unsigned int) * GNK_TICKETS));
+  GNK_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * 64));
+  *out = ctx;
+  return 0;
+}
+
+int gnk_destroy(gnk_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  gnk_comm_teardown(ctx);
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+  for (int b = 0; b < 2; ++b)
+    if (ctx->d_rbuf[b]) cudaFree(ctx->d_rbuf[b]);
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  delete ctx;
+  return 0;
+}
+
+int gnk_sm_count(gnk_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int64_t gnk_launch_count(gnk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

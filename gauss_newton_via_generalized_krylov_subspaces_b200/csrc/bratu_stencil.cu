@@ -40,10 +40,6 @@ __device__ __forceinline__ void store_pair(double* p, double a, double b) {
     *p = a;
 }
 
-struct RowTile {
-  int r0, r1;  // [r0, r1) rows handled by this CTA (relative to the first owned row)
-};
-
 // F = y - P(u), expu = e^u, loss = sum_owned F^2
 template <bool VEC>
 __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_bratu prm, const double* __restrict__ u,
@@ -224,8 +220,8 @@ int gnk_bratu_residual(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm
   const int R = lay->rows + 2 * depth;
   const int tr = pick_tr(ctx, gx, R, 1);
   dim3 grid(gx, (unsigned)ceil_div(R, tr));
-  GNK_REQUIRE((int64_t)grid.x * grid.y <= 8192 * 8, "gnk_bratu_residual: grid exceeds the partials scratch");
-  double* part = ctx->d_partials + (GNK_PARTIALS - 8192 * 8);
+  GNK_REQUIRE((int64_t)grid.x * grid.y <= 65536, "gnk_bratu_residual: grid exceeds the partials scratch");
+  double* part = ctx->d_partials + PART_RESID;
   if (vec)
     residual_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, d_u, d_y, d_F, d_expu, depth, tr, part,
                                                                  ctx->d_tickets + TK_RESID, d_loss);

@@ -32,6 +32,16 @@ struct gnk_ctx {
 constexpr int GNK_PARTIALS = 1 << 18;  // doubles (2 MiB)
 constexpr int GNK_TICKETS = 64;
 
+// regions inside gnk_ctx::d_partials (doubles); one per call site so that no two kernels share scratch
+constexpr int64_t PART_STATS = 0;                                   // 2 * grid
+constexpr int64_t PART_DOTS = 8192;                                 // grid(<=1184) * GNK_MAX_BASIS
+constexpr int64_t PART_UPDATE = PART_DOTS + 1184 * GNK_MAX_BASIS;   // 2 * grid
+constexpr int64_t PART_DOT1 = PART_UPDATE + 8192;                   // grid
+constexpr int64_t PART_CG = PART_DOT1 + 8192;                       // 2 * grid
+constexpr int64_t PART_SCAL = PART_CG + 8192;                       // 64 device scalars of the C-side loops
+constexpr int64_t PART_RESID = GNK_PARTIALS - 65536;                // residual kernel: one per CTA
+static_assert(PART_SCAL + 64 <= PART_RESID, "partials scratch overflow");
+
 enum TicketSlot { TK_RESID = 0, TK_STATS = 1, TK_DOTS = 2, TK_UPDATE = 3, TK_DOT1 = 4, TK_CG = 5 };
 
 void gnk_set_error(const std::string& s);

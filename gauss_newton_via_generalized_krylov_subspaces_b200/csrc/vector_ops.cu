@@ -283,14 +283,6 @@ inline int stream_grid(const gnk_ctx* ctx, int64_t items, int per_sm) {
 
 }  // namespace
 
-// Region offsets inside ctx->d_partials so that kernels running back to back on one stream never
-// share scratch with a still-running predecessor's "last CTA" phase (stream order already
-// serialises them; the split is belt and braces for multi-stream callers).
-static constexpr int64_t PART_STATS = 0;
-static constexpr int64_t PART_DOTS = 8192;
-static constexpr int64_t PART_UPDATE = PART_DOTS + 1184 * GNK_MAX_BASIS;
-static constexpr int64_t PART_DOT1 = PART_UPDATE + 8192;
-
 extern "C" {
 
 int gnk_combine(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_c,

@@ -1,0 +1,250 @@
+"""Gauss-Newton on generalized Krylov subspaces -- B200 mirror of the reference's ``gauss_newton_krylow.py``.
+
+Same signature, same iteration logic and the same counters as gauss_newton_krylow.py:39-145; the host keeps
+only the control flow.  Per outer iteration the device runs (all fp64, see csrc/):
+
+    J V_k            stencil / CSR SpMM                       (:86)
+    min|-JV d - r|   Householder TSQR of [-JV | r]            (:89, linear_least_squares :16-36)
+    Armijo trials    x = V_k(c + s d) ; fused residual+norm   (:91-93, armijo_goldstein.py:47-72)
+    c += s d ; stop test on s^2|d|^2 <= tol^2 |c_prev|^2      (:96-104)
+    J(x_new)         e^x is a by-product of the accepted trial (:107)
+    basis expansion  -J^T r, Gram-Schmidt vs V_k, normalise, append in place   (:110-124, krylow.py:55-73)
+    restart          V <- [x/|x|]                              (:135-136)
+
+and the host reads one small block of scalars per Armijo trial plus the breakdown flag.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .armijo_goldstein import armijo_device
+from .bratu_pde_problem import BratuDeviceProblem
+from .device import DeviceVector, HostCallableProblem, get_runtime, make_layout, ptr
+from .krylow import (GeneralizedKrylowSubspace, GeneralizedKrylowSubspaceBreakdown,
+                     GeneralizedKrylowSubspaceSpansEntireSpace, MAX_COLUMNS)
+from .partition import flat_layout_fields, round_up
+from .regression_result import RegressionResult
+
+_NB = _lib.GNK_MAX_BASIS
+# layout of the per-iteration scalar block (device, one D2H read per Armijo trial)
+_SC_LOSS = 2 * _NB + 8   # 2 doubles: sum(F^2) [, max|F|]
+_SC_CPREV = _SC_LOSS + 2  # sum(c_prev^2)
+_BLK = _SC_CPREV + 6
+
+
+def resolve_problem(res, jac, x0, args):
+    if BratuDeviceProblem.match(res, jac) and not args:
+        return BratuDeviceProblem(res, jac)
+    return HostCallableProblem(res, jac, x0, args)
+
+
+def tsqr_solve(rt, A, lda, n_rows, k, y, sign, out):
+    _lib.check(rt.lib.gnk_tsqr_ls(rt.ctx, ptr(A), lda, n_rows, k, ptr(y), float(sign), ptr(out), rt.stream),
+               "gnk_tsqr_ls")
+
+
+def linear_least_squares(A, y):
+    """Least squares solution of ||y - A x|| by Householder TSQR on the device (reference :16-36: economic QR,
+    a print per |r_kk| <= 1e-8, triangular solve).  A: (n, k) ndarray, y: (n,) ndarray -> x: (k,) ndarray."""
+    rt = get_runtime()
+    A = np.asarray(A, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    n, k = A.shape
+    if k + 1 > _NB:
+        raise _lib.GnkError(f"linear_least_squares supports at most {_NB - 1} columns")
+    lda = round_up(max(n, 1), 16)
+    dA = rt.zeros(lda * k)
+    for j in range(k):
+        rt.upload(np.ascontiguousarray(A[:, j]), dA[j * lda:j * lda + n])
+    dy = rt.zeros(lda)
+    rt.upload(y, dy[:n])
+    out = rt.zeros(2 * _NB + 8)
+    tsqr_solve(rt, dA, lda, n, k, dy, 1.0, out)
+    vals = rt.read(out, 2 * k + 4)
+    for _ in range(int(vals[k + 2])):
+        print("A is rank deficient")
+    return vals[:k].copy()
+
+
+def gauss_newton_krylow(
+    res: Callable,
+    x0,
+    jac: Callable,
+    krylow_restart: Optional[int] = None,
+    args: Tuple = (),
+    tol: float = 1e-8,
+    max_iter=100,
+    callback: Callable = lambda: None,
+    version: str = "res_old",
+    reorth_passes: int = 1,
+    x_on_device: bool = False,
+) -> RegressionResult:
+    """
+    Parameters
+    ----------
+    res: The residual function, called as res(x, *args).
+    x0: Initial guess of the regression parameters.
+    jac: Jacobian of residual function, called as jac(x, *args).
+    krylow_restart: If the basis gets larger than krylow_restart it is reset; None = never.
+    args: Additional arguments passed to res and jac.
+    tol: Tolerance for termination by the change of the parameters x.
+    max_iter: Maximum number of iterations.
+    callback: Called as callback(x=, nfev=, cg_iter=None) once per iteration; x converts lazily to ndarray.
+    version: One of ['res_old','res_new','jac_old_res_old','jac_old_res_new'] (see reference :61).
+    reorth_passes: 1 = the reference's single classical Gram-Schmidt pass (krylow.py:64); 2 = CGS2.
+    x_on_device: leave the solution in HBM (RegressionResult.x is then a lazy DeviceVector).  x0 may likewise be a
+        DeviceVector made by ``BratuPdeProblem.dev.resident(u0)``.
+
+    Returns
+    -------
+    RegressionResult
+    """
+    rt = get_runtime()
+    lib = rt.lib
+    success = False
+    x0_resident = isinstance(x0, DeviceVector) and x0._t is not None  # a start vector already in HBM
+    x0_host = None if x0_resident else np.asarray(x0, dtype=np.float64).reshape(-1)
+    prob = resolve_problem(res, jac, x0 if x0_resident else x0_host, args)
+    if krylow_restart is None:
+        krylow_restart = max_iter
+
+    krylow = GeneralizedKrylowSubspace(prob, capacity=min(max_iter, krylow_restart) + 1, reorth_passes=reorth_passes)
+    krylow._setup(prob.p_glob, prob.sol_fields, prob.sol, prob, krylow.capacity)
+    ld = krylow.ld
+    sol_lay = prob.sol
+
+    blk = rt.zeros(_BLK)            # [d(k) | g | resid2 | ndef | dnorm2 | diagR(k) ... | loss(2) | cprev2]
+    loss_slot = blk[_SC_LOSS:_SC_LOSS + 2]
+    c = rt.zeros(_NB)
+    one = rt.pinned(1)
+
+    def set_c0(value):
+        c.zero_()
+        one[0] = value
+        c[:1].copy_(one, non_blocking=True)
+
+    if x0_resident:
+        x_start = x0._t
+    else:
+        x_start = prob.new_sol()
+        prob.upload_x(x0_host, x_start)
+    set_c0(krylow.dev_start(x_start))
+
+    x_trial = prob.new_sol()
+    krylow.dev_combine(c, None, 0.0, x_trial)
+    is_bratu = isinstance(prob, BratuDeviceProblem)
+    if not is_bratu:  # residual-space size of a foreign callable is known after its first evaluation
+        r0 = np.asarray(res(prob.download_global(x_trial), *args), dtype=np.float64).reshape(-1)
+        prob._ensure_res_layout(r0.shape[0])
+    F_cur, F_trial = prob.new_res(), prob.new_res()
+    res_off = prob.res_fields["off"]
+    n_res_own = prob.res_fields["n_own"]
+    ldjv = round_up(max(n_res_own, 1), 16)
+    use_aux = is_bratu and prob.pb.LAMBDA != 0
+    aux = [prob.new_sol() for _ in range(3)] if use_aux else [None, None, None]  # e^x: J_cur, trial, spare
+    hx = prob.d.halo_exchange if (is_bratu and prob.distributed) else None
+
+    if is_bratu:
+        prob.residual(x_trial, F_cur, loss_slot, aux=None)
+    else:
+        rt.upload(r0, F_cur[:n_res_own])
+        prob.sumsq(F_cur, loss_slot, prob.res_lay)
+    nfev = 1
+    prev_loss = float(rt.read(loss_slot, 1)[0])
+    jac_ev = prob.jacobian(x_start, aux=None)  # note: at x0 itself (reference :78), not at V c
+    if use_aux:
+        aux[0] = jac_ev.expu
+    njev = 1
+
+    JV = None
+    jv_cap = 0
+    state = {}
+
+    for iter in range(1, max_iter):
+        k = krylow.k
+        if k > jv_cap:
+            jv_cap = min(MAX_COLUMNS, max(krylow.cap, k))
+            JV = rt.empty(jv_cap * ldjv)
+        # projected operator and projected least squares  (:86-89)
+        with rt.mark("spmm", 8.0 * n_res_own * (2 * k + 1)):
+            jac_ev.matmat(krylow.V, ld, k, JV, ldjv)
+        with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
+            tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk)
+        _lib.check(lib.gnk_dot(rt.ctx, k, ptr(c), ptr(c), ptr(blk, _SC_CPREV), rt.stream), "gnk_dot")
+
+        # Armijo-Goldstein in coordinate space  (:91-93)
+        def trial_loss(s):
+            krylow.dev_combine(c, blk, s, x_trial)
+            with rt.mark("residual", 32.0 * n_res_own):
+                prob.residual(x_trial, F_trial, loss_slot, aux=aux[1])
+            state["vals"] = rt.read(blk, _BLK)
+            return float(state["vals"][_SC_LOSS])
+
+        step_length, nfev_delta = armijo_device(
+            trial_loss, prev_loss, lambda: float(state["vals"][k]), lambda: float(np.sqrt(state["vals"][k + 3])))
+        nfev += nfev_delta
+        vals = state["vals"]
+        for _ in range(int(vals[k + 2])):
+            print("A is rank deficient")
+        squared_sum_d = float(vals[k + 3])
+        squared_sum_x_prev = float(vals[_SC_CPREV])
+
+        # c += s d  (:98)
+        _lib.check(lib.gnk_axpby(rt.ctx, k, 1.0, ptr(c), float(step_length), ptr(blk), ptr(c), rt.stream), "gnk_axpby")
+
+        xv = DeviceVector(prob, x_trial, prob.p_glob)
+        callback(x=xv, nfev=nfev, cg_iter=None)
+        xv.detach_if_shared()
+        del xv
+
+        if step_length**2 * squared_sum_d <= tol**2 * squared_sum_x_prev:
+            success = True
+            break
+
+        jac_ev_old = jac_ev
+        jac_ev = prob.jacobian(x_trial, aux=aux[1])  # e^x came out of the accepted trial
+        njev += 1
+
+        try:
+            if version == "res_old":
+                krylow.dev_update(jac_ev, F_cur, hx)
+            elif version == "res_new":
+                krylow.dev_update(jac_ev, F_trial, hx)
+            elif version == "jac_old_res_old":
+                krylow.dev_update(jac_ev_old, F_cur, hx)
+            elif version == "jac_old_res_new":
+                krylow.dev_update(jac_ev_old, F_trial, hx)
+            else:
+                raise ValueError(
+                    "Variable version must be in ['res_old','res_new','jac_old_res_old','jac_old_res_new']"
+                )
+            c[krylow.k - 1:krylow.k].zero_()  # x_coordinate = np.append(x_coordinate, 0)   (:124)
+        except GeneralizedKrylowSubspaceBreakdown:
+            print(
+                f"Generalized krylow subspace breakdown at iteration = {iter}, basis.shape = ({prob.p_glob}, {krylow.k})"
+            )
+        except GeneralizedKrylowSubspaceSpansEntireSpace:
+            print(
+                f"Warning: The genearlized krylow subspace is now identical to the whole parameter space at iteration = {iter}"
+            )
+
+        # the trial becomes the current point
+        F_cur, F_trial = F_trial, F_cur
+        prev_loss = float(vals[_SC_LOSS])
+        if use_aux:
+            aux[0], aux[1], aux[2] = aux[1], aux[2], aux[0]
+        del jac_ev_old
+
+        if iter % krylow_restart == 0:  # (:135-136)  x = V c equals the accepted trial point bit for bit
+            set_c0(krylow.dev_start(x_trial))
+
+    if not success:
+        print("Warning: The gauss_newton_krylow algorithm reached maximal iteration bound before terminating!")
+
+    krylow.dev_combine(c, None, 0.0, x_trial)
+    x_final = DeviceVector(prob, x_trial, prob.p_glob) if x_on_device else prob.download_global(x_trial)
+    return RegressionResult("gauss newton krylow", x_final, success, nfev, njev, iter)

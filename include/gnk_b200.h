@@ -155,7 +155,7 @@ typedef struct {
  * quirk (preconditioner == 0 first runs an unpreconditioned CG whose result is discarded and whose
  * iterations are added to *iters).  d_y: residual vector (stencil: stored column, halo >= 1 valid;
  * CSR: n_res doubles).  d_x: result (stencil: stored column; CSR: p doubles).  d_work: at least
- * 6 stored columns (stencil) / 5*p + n_res doubles (CSR).  Synchronises the stream. */
+ * 7 stored columns (stencil) / 7 * roundup16(max(p, n_res)) doubles (CSR).  Synchronises the stream. */
 int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, double rtol, int preconditioner,
              double* d_x, double* d_work, int64_t* iters, void* stream);
 

@@ -1,0 +1,354 @@
+"""Kernel-level parity (-m gpu): every C-ABI entry point against the oracle / the reference's golden vectors.
+
+Tolerances: all arithmetic is fp64; a kernel differs from the numpy/scipy evaluation only by summation order
+and FMA contraction, so element-wise results are compared at 1e-13 relative to the vector's max-norm and
+reductions over n terms at 1e-12 relative.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import Golden, rel  # noqa: E402
+from oracle import gnk_oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def g():
+    import gauss_newton_via_generalized_krylov_subspaces_b200 as pkg
+    import gauss_newton_via_generalized_krylov_subspaces_b200.device as device
+    if os.environ.get("GNK_TEST_MOCK"):  # debugging aid for the test code itself; never set by the driver
+        import mock_backend
+        mock_backend.install()
+        return pkg
+    device._runtime = None
+    pkg.get_runtime()  # raises without CUDA + the built library: no fallback
+    return pkg
+
+
+def _lib_mods():
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import _lib, device
+    return _lib, device
+
+
+def test_library_is_native(g):
+    if os.environ.get("GNK_TEST_MOCK"):
+        pytest.skip("mock")
+    rt = g.get_runtime()
+    assert rt.lib.gnk_abi_version() == 1
+    assert rt.lib.gnk_sm_count(rt.ctx) >= 100
+    import torch
+    assert torch.cuda.get_device_capability(rt.device_index)[0] >= 10
+
+
+# ------------------------------------------------------------------------------------------------
+# Bratu stencil kernels vs the reference's scipy operators (golden) and the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["g11", "g10", "g26lin", "g33h1", "g101"])
+def test_stencil_against_reference_golden(g, tag):
+    z = Golden("kernels")
+    G, a, l, h = z[f"{tag}/params"]
+    pb = g.BratuPdeProblem(int(G), a, l, grid_resolution=None if h < 0 else h)
+    u, V, r = z[f"{tag}/u"], z[f"{tag}/V"], z[f"{tag}/r"]
+    assert rel(pb.u_true, z[f"{tag}/u_true"]) == 0.0
+    assert rel(pb.pde_operator(u), z[f"{tag}/P"]) < 1e-13
+    J = pb.make_jac()(u)
+    assert rel(J @ V, z[f"{tag}/JV"]) < 1e-13
+    assert rel(J.T @ r, z[f"{tag}/JTr"]) < 1e-13
+    assert rel((-1 * J) @ r, -(J @ r)) == 0.0
+    # diag(J^T J) through the C ABI
+    _lib, device = _lib_mods()
+    d = pb.dev
+    out = d.new_col()
+    _lib.check(d.rt.lib.gnk_stencil_normal_diag(d.rt.ctx, C.byref(d.lay), C.byref(d.prm), device.ptr(J.expu),
+                                                device.ptr(out), d.rt.stream))
+    assert rel(d.download_global(out), z[f"{tag}/JTJdiag"]) < 1e-13
+
+
+@pytest.mark.parametrize("G,lam", [(12, 10.0), (9, 10.0), (130, 10.0), (258, 3.0), (131, 0.0)])
+@pytest.mark.parametrize("depth", [0, 1])
+def test_fused_residual(g, G, lam, depth):
+    """F, e^u and sum(F^2) in one pass, on owned rows and on the halo rows (zero outside the domain)."""
+    _lib, device = _lib_mods()
+    o = orc.BratuOracle(G, 5, lam)
+    pb = g.BratuPdeProblem(G, 5, lam)
+    rs = np.random.RandomState(G)
+    u = 0.5 * rs.normal(size=o.n)
+    y = rs.normal(size=o.n)
+    d = pb.dev
+    x, ycol, F, E = d.new_col(), d.new_col(), d.new_col(), d.new_col()
+    d.upload_x(u, x)
+    d.upload_x(y, ycol)
+    loss = d.rt.zeros(2)
+    d.residual_into(x, ycol, F, E, loss, depth=depth)
+    Fref = y - o.operator(u)
+    assert rel(d.download_global(F), Fref) < 1e-13
+    if lam != 0:
+        assert rel(d.download_global(E), np.exp(u)) < 1e-14
+    got = float(d.rt.read(loss, 1)[0])
+    assert abs(got - np.sum(Fref ** 2)) <= 1e-12 * np.sum(Fref ** 2)
+    # single rank: the halo rows lie outside the domain -> F must be exactly zero there
+    f = d.fields
+    full = d.rt.download(F)
+    assert np.all(full[:f["off"]] == 0.0) and np.all(full[f["off"] + f["n_own"]:] == 0.0)
+
+
+def test_residual_is_zero_at_solution(g):
+    pb = g.BratuPdeProblem(200, 5, 10)
+    y = pb.pde_operator(pb.u_true)
+    r = pb.make_res(y)(pb.u_true)
+    assert np.max(np.abs(r)) == 0.0  # the same kernel evaluated both sides
+
+
+# ------------------------------------------------------------------------------------------------
+# basis kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k", [(1, 1), (2, 1), (7, 3), (1000, 7), (1001, 16), (4097, 17), (100003, 33), (65536, 103)])
+def test_basis_kernels(g, n, k):
+    _lib, device = _lib_mods()
+    from gauss_newton_via_generalized_krylov_subspaces_b200.partition import flat_layout_fields
+    rt = g.get_runtime()
+    lib = rt.lib
+    f = flat_layout_fields(n)
+    lay = device.make_layout(f)
+    ld = f["ld"]
+    rs = np.random.RandomState(n + k)
+    Vh = rs.normal(size=(k, n))
+    c, dd, w = rs.normal(size=k), rs.normal(size=k), rs.normal(size=n)
+    V = rt.zeros(k * ld)
+    for j in range(k):
+        rt.upload(Vh[j], V[j * ld:j * ld + n])
+    dc, ddv, dw, x = rt.zeros(128), rt.zeros(128), rt.zeros(ld), rt.zeros(ld)
+    rt.upload(c, dc[:k])
+    rt.upload(dd, ddv[:k])
+    rt.upload(w, dw[:n])
+    # combine
+    _lib.check(lib.gnk_combine(rt.ctx, C.byref(lay), device.ptr(V), k, device.ptr(dc), device.ptr(ddv), 0.25,
+                               device.ptr(x), rt.stream))
+    ref = (c + 0.25 * dd) @ Vh
+    assert rel(rt.download(x[:n]), ref) < 1e-13
+    _lib.check(lib.gnk_combine(rt.ctx, C.byref(lay), device.ptr(V), k, device.ptr(dc), None, 0.0, device.ptr(x),
+                               rt.stream))
+    assert rel(rt.download(x[:n]), c @ Vh) < 1e-13
+    # stats + normalize
+    st = rt.zeros(2)
+    flag = rt.zeros(1, dtype=rt.torch.int32)
+    _lib.check(lib.gnk_norm_stats(rt.ctx, C.byref(lay), device.ptr(dw), device.ptr(st), rt.stream))
+    s = rt.read(st, 2)
+    assert abs(s[0] - np.sum(w * w)) <= 1e-13 * np.sum(w * w) and s[1] == np.max(np.abs(w))
+    out = rt.zeros(ld)
+    _lib.check(lib.gnk_normalize(rt.ctx, C.byref(lay), device.ptr(dw), device.ptr(st), 1e-8, device.ptr(out),
+                                 device.ptr(flag), rt.stream))
+    assert rt.read_i32(flag)[0] == 0
+    assert rel(rt.download(out[:n]), w / np.linalg.norm(w)) < 1e-15
+    tiny = rt.zeros(ld)
+    rt.upload(1e-9 * w / np.max(np.abs(w)), tiny[:n])
+    _lib.check(lib.gnk_norm_stats(rt.ctx, C.byref(lay), device.ptr(tiny), device.ptr(st), rt.stream))
+    _lib.check(lib.gnk_normalize(rt.ctx, C.byref(lay), device.ptr(tiny), device.ptr(st), 1e-8, device.ptr(out),
+                                 device.ptr(flag), rt.stream))
+    assert rt.read_i32(flag)[0] == 1  # breakdown: max|w| <= 1e-8 (krylow.py:66)
+    # Gram-Schmidt halves
+    h = rt.zeros(128)
+    _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(lay), device.ptr(V), k, device.ptr(dw), device.ptr(h), rt.stream))
+    href = Vh @ w
+    assert rel(rt.read(h, k), href) < 1e-12
+    rt.upload(href, h[:k])
+    _lib.check(lib.gnk_cgs_update(rt.ctx, C.byref(lay), device.ptr(V), k, device.ptr(h), device.ptr(dw),
+                                  device.ptr(st), rt.stream))
+    wref = w - href @ Vh
+    assert rel(rt.download(dw[:n]), wref) < 1e-12
+    s = rt.read(st, 2)
+    assert abs(s[0] - np.sum(wref ** 2)) <= 1e-12 * np.sum(wref ** 2)
+    assert abs(s[1] - np.max(np.abs(wref))) <= 1e-12 * np.max(np.abs(wref))
+    # axpby / dot
+    _lib.check(lib.gnk_axpby(rt.ctx, n, 2.0, device.ptr(dw), -0.5, device.ptr(x), device.ptr(out), rt.stream))
+    assert rel(rt.download(out[:n]), 2.0 * wref - 0.5 * (c @ Vh)) < 1e-13
+    _lib.check(lib.gnk_dot(rt.ctx, n, device.ptr(dw), device.ptr(x), device.ptr(st), rt.stream))
+    assert abs(rt.read(st, 1)[0] - np.dot(wref, c @ Vh)) <= 1e-11 * np.linalg.norm(wref) * np.linalg.norm(c @ Vh)
+
+
+def test_reductions_are_deterministic(g):
+    _lib, device = _lib_mods()
+    from gauss_newton_via_generalized_krylov_subspaces_b200.partition import flat_layout_fields
+    rt = g.get_runtime()
+    n, k = 1 << 20, 9
+    f = flat_layout_fields(n)
+    lay = device.make_layout(f)
+    V = rt.torch.randn(k * f["ld"], dtype=rt.torch.float64, device=rt.device)
+    w = rt.torch.randn(f["ld"], dtype=rt.torch.float64, device=rt.device)
+    h = rt.zeros(128)
+    outs = []
+    for _ in range(3):
+        _lib.check(rt.lib.gnk_cgs_dots(rt.ctx, C.byref(lay), device.ptr(V), k, device.ptr(w), device.ptr(h), rt.stream))
+        outs.append(rt.read(h, k))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# Householder TSQR least squares
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k", [(2, 1), (3, 2), (5, 4), (40, 7), (300, 8), (1000, 15), (5000, 16), (100000, 30),
+                                 (20000, 31), (7777, 40), (30000, 63), (9000, 64), (4000, 100), (250, 103)])
+def test_tsqr_least_squares(g, n, k):
+    rs = np.random.RandomState(n * 7 + k)
+    A = rs.normal(size=(n, k)) @ (np.eye(k) + 0.3 * rs.normal(size=(k, k)))
+    y = rs.normal(size=n)
+    x = g.linear_least_squares(A, y)
+    xr = np.linalg.lstsq(A, y, rcond=None)[0]
+    cond = np.linalg.cond(A)
+    assert rel(x, xr) < 1e-13 * max(cond, 10.0)
+
+
+def test_tsqr_scalar_block_and_rank_deficiency(g, capsys):
+    _lib, device = _lib_mods()
+    from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve
+    rt = g.get_runtime()
+    n, k = 5000, 6
+    rs = np.random.RandomState(5)
+    A = rs.normal(size=(n, k))
+    y = rs.normal(size=n)
+    lda = 5008
+    dA = rt.zeros(lda * k)
+    for j in range(k):
+        rt.upload(A[:, j].copy(), dA[j * lda:j * lda + n])
+    dy = rt.zeros(lda)
+    rt.upload(y, dy[:n])
+    out = rt.zeros(256)
+    tsqr_solve(rt, dA, lda, n, k, dy, -1.0, out)  # min || -A d - y ||
+    v = rt.read(out, 2 * k + 4)
+    d = np.linalg.lstsq(-A, y, rcond=None)[0]
+    assert rel(v[:k], d) < 1e-12
+    assert abs(v[k] - np.sum((A @ d) ** 2)) < 1e-11 * np.sum((A @ d) ** 2)       # ||R d||^2 = ||A d||^2
+    assert abs(v[k + 1] - np.sum((-A @ d - y) ** 2)) < 1e-11 * np.sum(y ** 2)     # LS residual
+    assert v[k + 2] == 0 and abs(v[k + 3] - np.sum(d * d)) < 1e-12 * np.sum(d * d)
+    assert np.allclose(np.abs(v[k + 4:2 * k + 4]), np.abs(np.diag(np.linalg.qr(A, mode="r"))), rtol=1e-11)
+    # a repeated column -> exactly one |r_kk| <= 1e-8, one print (gauss_newton_krylow.py:32-34)
+    A2 = A.copy()
+    A2[:, 4] = A2[:, 1]
+    g.linear_least_squares(A2, y)
+    assert capsys.readouterr().out.count("A is rank deficient") == 1
+
+
+def test_tsqr_norm_preservation_large(g):
+    """size-independent property at the benchmark's row count: ||R||_F = ||[A|y]||_F and R^T R = M^T M."""
+    _lib, device = _lib_mods()
+    from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve
+    rt = g.get_runtime()
+    n, k = 4096 * 4096, 12
+    A = rt.torch.randn(k * n, dtype=rt.torch.float64, device=rt.device)
+    y = rt.torch.randn(n, dtype=rt.torch.float64, device=rt.device)
+    out = rt.zeros(256)
+    tsqr_solve(rt, A, n, n, k, y, 1.0, out)
+    v = rt.read(out, 2 * k + 4)
+    M = rt.torch.cat([A.view(k, n), y.view(1, n)], 0)
+    Gm = (M @ M.T).cpu().numpy()          # torch here is the checker, not the product
+    d = np.linalg.solve(Gm[:k, :k], Gm[:k, k])
+    assert rel(v[:k], d) < 1e-9
+    assert abs(v[k] + v[k + 1] - Gm[k, k]) < 1e-12 * Gm[k, k]   # ||Q^T y||^2 + resid^2 = ||y||^2
+    assert np.allclose(v[k + 4:2 * k + 4] ** 2, np.diag(np.linalg.cholesky(Gm[:k, :k])) ** 2, rtol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------
+# CSR kernels and CGLS
+# ------------------------------------------------------------------------------------------------
+def test_csr_kernels_rosenbrock(g):
+    _lib, device = _lib_mods()
+    import scipy.sparse as sp
+    z = Golden("kernels")
+    x = z["rosen/x"]
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
+    assert rel(rp.res(x), z["rosen/res"]) == 0.0
+    J = sp.csr_array(rp.jac(x))
+    Jg = sp.csr_array((z["rosen/data"], z["rosen/indices"], z["rosen/indptr"]), shape=J.shape)
+    assert abs(J - Jg).max() == 0.0
+    rt = g.get_runtime()
+    op = device.CsrJacobian(rt, rp.jac(x), True)
+    rs = np.random.RandomState(0)
+    V = rs.normal(size=(3, 1000))
+    dV = rt.zeros(3 * 1008)
+    for j in range(3):
+        rt.upload(V[j], dV[j * 1008:j * 1008 + 1000])
+    JV = rt.zeros(3 * 2000)
+    op.matmat(dV, 1008, 3, JV, 2000)
+    got = rt.download(JV).reshape(3, 2000)[:, :1998]
+    assert rel(got, (J @ V.T).T) < 1e-14
+    r = rs.normal(size=1998)
+    dr, w = rt.zeros(2000), rt.zeros(1008)
+    rt.upload(r, dr[:1998])
+    op.neg_rmatvec(dr, w)
+    assert rel(rt.download(w[:1000]), -(J.T @ r)) < 1e-14
+    ss = rt.zeros(1008)
+    _lib.check(rt.lib.gnk_csr_row_sumsq(rt.ctx, 1000, device.ptr(op.rowptr_t), device.ptr(op.val_t), device.ptr(ss),
+                                        rt.stream))
+    assert rel(rt.download(ss[:1000]), (J.T @ J).diagonal()) < 1e-14
+
+
+@pytest.mark.parametrize("precond", [True, False])
+def test_cgls_stencil_and_csr(g, precond):
+    o = orc.BratuOracle(41, 5, 10)
+    pb = g.BratuPdeProblem(41, 5, 10)
+    rs = np.random.RandomState(1)
+    u = 0.2 * rs.normal(size=o.n)
+    y = rs.normal(size=o.n)
+    xr, itr = orc.cgls(-1 * o.make_jac()(u), y, preconditioner=precond)
+    xg, itg = g.cg_least_squares(-1 * pb.make_jac()(u), y, preconditioner=precond)
+    assert abs(itg - itr) <= max(2, itr // 50)
+    assert rel(xg, xr) < 1e-3  # both stop at rtol=1e-4 on the normal-equation residual
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
+    x = 1 + 0.1 * rs.normal(size=1000)
+    r = rp.res(x)
+    xr, itr = orc.cgls(-1 * orc.rosenbrock_jac(x), r, preconditioner=precond)
+    xg, itg = g.cg_least_squares(-1 * rp.jac(x), r, preconditioner=precond)
+    assert abs(itg - itr) <= 2
+    assert rel(xg, xr) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# public building blocks with the reference's signatures
+# ------------------------------------------------------------------------------------------------
+def test_generalized_krylow_subspace_public_api(g):
+    rs = np.random.RandomState(3)
+    x0 = rs.normal(size=500)
+    ks = g.GeneralizedKrylowSubspace()
+    c = ks.start(x0)
+    assert c.shape == (1,) and abs(c[0] - np.linalg.norm(x0)) < 1e-13 * c[0]
+    assert rel(ks.x(c), x0) < 1e-15
+    V = [x0 / np.linalg.norm(x0)]
+    for it in range(4):
+        J = rs.normal(size=(700, 500))
+        r = rs.normal(size=700)
+        ks.update(J, r)
+        w = -(J.T @ r)
+        Vm = np.array(V).T
+        w = w - Vm @ (Vm.T @ w)
+        V.append(w / np.linalg.norm(w))
+    B = ks.basis
+    assert B.shape == (500, 5) and rel(B, np.array(V).T) < 1e-12
+    assert ks.evaluate(lambda x, a: a * np.sum(x), np.ones(5), 2.0) == pytest.approx(2.0 * np.sum(B @ np.ones(5)))
+    with pytest.raises(ValueError):
+        g.GeneralizedKrylowSubspace().start(np.zeros(10))
+    with pytest.raises(g.GeneralizedKrylowSubspaceBreakdown):
+        ks.update(np.zeros((700, 500)), r)
+    small = g.GeneralizedKrylowSubspace()
+    small.start(np.array([1.0]))
+    with pytest.raises(g.GeneralizedKrylowSubspaceSpansEntireSpace):
+        small.update(np.array([[1.0], [2.0]]), np.array([1.0, 1.0]))
+
+
+def test_armijo_goldstein_public_api(g):
+    def res(x, t):
+        return np.array([x[0] + 1, t * x[0] ** 2 + x[0] - 1])
+
+    x = np.array([1.0])
+    J = np.array([[1.0], [2 * 5 * x[0] + 1]])
+    r = res(x, 5)
+    d = np.linalg.lstsq(-J, r, rcond=None)[0]
+    s, rn, it = g.armijo_goldstein(res, x, r, J, (5,), d)
+    so, rno, ito = orc.armijo(res, x, r, np.sum((J @ d) ** 2), (5,), d)
+    assert (s, it) == (so, ito) and np.array_equal(rn, rno)
+    with pytest.raises(g.StepLengthConvergenceError):
+        g.armijo_goldstein(res, x, r, J, (5,), -d)
