@@ -233,6 +233,36 @@ def g4097():
     ), y_sample=y[sample_idx(y.shape[0])], u0_sample=u0[sample_idx(u0.shape[0])])
 
 
+def sensitivity(G, name, runs_kw):
+    """The reference against ITSELF when the start vector u0 is perturbed by one unit in the last place (relative
+    2^-52, random signs, seed 7).  The deviation of the perturbed trace from the unperturbed one is the conditioning of
+    the reference's trajectory: no independent implementation (different summation order, FMA contraction, another
+    exp) can be expected to reproduce the iterates more closely than a small multiple of this envelope.  (Perturbing y
+    instead under-estimates it: |y| << |res(u0)| on these noise-dominated starts.)"""
+    pb, y, res, jac, err, u0 = bratu_setup(G, 5, 10)
+    sgn = np.random.RandomState(7).choice([-1.0, 1.0], size=u0.shape[0])
+    u0p = u0 * (1.0 + sgn * 2.0 ** -52)
+    out = {}
+    for rname, kw in runs_kw.items():
+        out[rname] = run(gauss_newton_krylow, res, u0p, jac, err, loss_every=0, **kw)
+    save(name, out)
+
+
+def sens101():
+    sensitivity(101, "bratu_g101_sens", dict(gnk_res_old=dict(max_iter=100),
+                                             gnk_restart30=dict(max_iter=100, krylow_restart=30)))
+
+
+def sens1025():
+    sensitivity(1025, "bratu_g1025_sens", dict(gnk_k30=dict(max_iter=31),
+                                               gnk_restart30=dict(max_iter=100, krylow_restart=30)))
+
+
+def sens4097():
+    sensitivity(4097, "bratu_g4097_sens", dict(gnk_k30=dict(max_iter=31)))
+
+
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["small"]:
-        dict(small=small, g1025=g1025, g4097=g4097, kernels=kernels_fixture)[what]()
+        dict(small=small, g1025=g1025, g4097=g4097, kernels=kernels_fixture, sens101=sens101, sens1025=sens1025,
+             sens4097=sens4097)[what]()

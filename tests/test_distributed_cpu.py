@@ -1,0 +1,75 @@
+"""world_size 2 and 3 over gloo on the CPU: the sharded (row-slab) path of the host logic -- slab layout, depth-2
+halos, the single halo exchange per outer iteration, rank-ordered reductions, the gathered TSQR R factors -- with
+the numpy mock standing in for the CUDA kernels and NCCL (tests/mock_backend.py).  The N>1 CUDA+NCCL path itself is
+exercised on the GPU box (tests/test_gpu_multi.py via torchrun) and by bench.py --gpus N.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, G, restart, max_iter, version, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mock_backend
+    mock_backend.install()
+    import gauss_newton_via_generalized_krylov_subspaces_b200 as g
+    from golden_util import Golden, Recorder
+
+    gd = Golden(f"bratu_g{G}")
+    pb = g.BratuPdeProblem(G, 5, 10)
+    assert pb.dev.fields["rows"] >= 2 and g.get_runtime().world == world
+    y = pb.pde_operator(pb.u_true)                      # sharded stencil + all-gather of the owned parts
+    res, jac, err = pb.make_res(gd["y"]), pb.make_jac(), pb.make_error()
+    J = jac(gd["u0"])
+    v = np.random.RandomState(0).normal(size=pb.n)
+    gr = gd.run("gnk_res_old")
+    rec = Recorder(gr["sample_idx"], err)
+    out = g.gauss_newton_krylow(res, gd["u0"], jac, callback=rec, krylow_restart=restart, max_iter=max_iter,
+                                version=version)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), y=y, Jv=J @ v, JTv=J.T @ v, xs=np.array(rec.xs),
+             xnorm=np.array(rec.xnorm), nfev=np.array(rec.nfev), x=out.x, nit=out.nit, nrev=out.nrev)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_gnk_matches_reference_golden(world, tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import Golden, rel
+    from oracle import gnk_oracle as orc
+    G = 34  # m = 33 grid rows: uneven slabs (17+16 / 11+11+11), odd row length
+    mp.spawn(_worker, args=(world, _free_port(), G, 12, 40, "res_old", str(tmp_path)), nprocs=world, join=True)
+    gd = Golden(f"bratu_g{G}")
+    gr = gd.run("gnk_res_old")
+    o = orc.BratuOracle(G, 5, 10)
+    Jo = o.make_jac()(gd["u0"])
+    v = np.random.RandomState(0).normal(size=o.n)
+    outs = [np.load(os.path.join(tmp_path, f"r{r}.npz")) for r in range(world)]
+    for z in outs:
+        assert rel(z["y"], gd["y"]) < 1e-14                      # halo rows were filled correctly
+        assert rel(z["Jv"], Jo @ v) < 1e-14 and rel(z["JTv"], Jo.T @ v) < 1e-14
+        assert int(z["nit"]) == int(gr["nit"]) and int(z["nrev"]) == int(gr["nfev"])
+        assert list(z["nfev"]) == list(gr["nfev_cb"])
+        scale = np.max(np.abs(gr["xs"]), axis=1, keepdims=True)
+        assert np.max(np.abs(z["xs"][:12] - gr["xs"][:12]) / scale[:12]) < 1e-10       # before the first restart
+        assert np.max(np.abs(z["xs"] - gr["xs"]) / scale) < 1e-8                       # restarts amplify rounding
+    for z in outs[1:]:                                           # every rank holds the same global result, bit for bit
+        assert np.array_equal(z["x"], outs[0]["x"]) and np.array_equal(z["xnorm"], outs[0]["xnorm"])

@@ -1,0 +1,191 @@
+"""CPU tests of everything that is not a CUDA kernel: the C-ABI library's exported surface, the slab partition, and
+the Python host logic (solver control flow, buffer rotation, counters, messages) driven through the numpy mock of
+the C ABI (tests/mock_backend.py -- test infrastructure, injected explicitly; the product has no CPU path).
+"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from golden_util import Golden, Recorder, check_trace, rel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "gauss_newton_via_generalized_krylov_subspaces_b200")
+
+
+# ------------------------------------------------------------------------------------------------
+# the shared library: loads, exports every symbol include/gnk_b200.h declares, and nothing computes without a GPU
+# ------------------------------------------------------------------------------------------------
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "gnk_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gnk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_the_header_surface():
+    import __graft_entry__
+    __graft_entry__.build()
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import _lib
+    lib = _lib.load()
+    declared = _header_functions()
+    assert len(declared) >= 25
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (gnk_[a-z0-9_]+)", nm))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert set(declared) == set(_lib.SIGNATURES), (set(declared) ^ set(_lib.SIGNATURES))
+    assert lib.gnk_abi_version() == 1
+    # sm_100a code is in the fat binary
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import gauss_newton_via_generalized_krylov_subspaces_b200 as g
+    import gauss_newton_via_generalized_krylov_subspaces_b200.device as device
+    device._runtime = None
+    pb = g.BratuPdeProblem(11, 5, 10)
+    with pytest.raises(Exception) as ei:
+        pb.pde_operator(np.zeros(100))
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+    with pytest.raises(Exception):
+        g.gauss_newton_krylow(lambda x: x, np.ones(3), lambda x: np.eye(3), callback=lambda **k: None)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", "").replace("CPU oracle", "") or f == "__init__.py", f
+                assert "mock_backend" not in text, f
+
+
+# ------------------------------------------------------------------------------------------------
+# slab partition (pure integer logic)
+# ------------------------------------------------------------------------------------------------
+def test_slab_partition():
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import partition as P
+    for m in (1, 2, 7, 33, 100, 1024, 4096, 8192):
+        for world in (1, 2, 3, 4, 8):
+            bounds = [P.slab_bounds(m, world, r) for r in range(world)]
+            assert bounds[0][0] == 0 and bounds[-1][1] == m
+            assert all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in bounds]
+            assert max(sizes) - min(sizes) <= 1
+            assert sum(P.all_counts(m, world)) == m * m
+    f = P.stencil_layout_fields(4096, 8, 3)
+    assert (f["rows"], f["off"], f["n_own"], f["has_lo"], f["has_hi"]) == (512, 8192, 512 * 4096, 1, 1)
+    assert f["ld"] % 16 == 0 and f["ld"] >= (512 + 4) * 4096
+    with pytest.raises(ValueError):
+        P.stencil_layout_fields(8, 8, 0)   # 1-row slabs are thinner than the halo
+    x = np.arange(7 * 7, dtype=np.float64)
+    f = P.stencil_layout_fields(7, 3, 1)   # rows [3,5)
+    col = np.full(f["ld"], -1.0)
+    P.stored_column_from_global(x, f, col[:(f["rows"] + 4) * 7])
+    assert np.array_equal(col[:(f["rows"] + 4) * 7], x[7:49])   # rows 1..6
+    f = P.stencil_layout_fields(7, 3, 0)   # rows [0,3): two zero halo rows in front
+    col = np.full(f["ld"], -1.0)
+    P.stored_column_from_global(x, f, col[:(f["rows"] + 4) * 7])
+    assert np.all(col[:14] == 0) and np.array_equal(col[14:49], x[:35])
+
+
+# ------------------------------------------------------------------------------------------------
+# host logic through the mock
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture()
+def g():
+    import mock_backend
+    mock_backend.install()
+    import gauss_newton_via_generalized_krylov_subspaces_b200 as pkg
+    yield pkg
+    mock_backend.uninstall()
+
+
+def test_host_gnk_bratu(g, capsys):
+    gd = Golden("bratu_g101")
+    pb = g.BratuPdeProblem(101, 5, 10)
+    assert rel(pb.pde_operator(pb.u_true), gd["y"]) < 1e-14
+    res, jac, err = pb.make_res(gd["y"]), pb.make_jac(), pb.make_error()
+    for rname, kw, tol in (("gnk_res_old", dict(max_iter=30), 1e-12),
+                           ("gnk_jac_old_res_new", dict(max_iter=25, version="jac_old_res_new"), 1e-12),
+                           ("gnk_restart7_res_new", dict(max_iter=40, krylow_restart=7, version="res_new"), 1e-8)):
+        gr = gd.run(rname)
+        rec = Recorder(gr["sample_idx"], err)
+        out = g.gauss_newton_krylow(res, gd["u0"], jac, callback=rec, **kw)
+        check_trace(rec, gr, tol, upto=len(rec.xnorm))
+        assert out.nrev == out.nit + 1 and out.njev == out.nit + 1 and not out.success
+    assert "reached maximal iteration bound" in capsys.readouterr().out
+
+
+def test_host_gn_and_foreign_callables(g):
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
+    gd = Golden("rosenbrock")
+    for tag, rname, kw in (("i", "gnk_res_new", dict(version="res_new")), ("iii", "gnk_res_old", {})):
+        gr = gd.run(f"{tag}_{rname}")
+        rec = Recorder(gr["sample_idx"], rp.error)
+        out = g.gauss_newton_krylow(rp.res, gd["x0_" + tag], rp.jac, callback=rec, **kw)
+        check_trace(rec, gr, 1e-10)
+        assert (out.nit, out.nrev, out.success) == (int(gr["nit"]), int(gr["nfev"]), True)
+    gr = gd.run("i_gn")
+    rec = Recorder(gr["sample_idx"], rp.error)
+    out = g.gauss_newton(rp.res, gd["x0_i"], rp.jac, callback=rec)
+    assert (out.nit, out.nrev, out.njev) == (5, 6, 5) and list(rec.cg) == list(gr["cg_iter"])
+
+
+def test_host_step_length_plugins_and_errors(g):
+    def pres(x, tau):
+        return np.array([x[0] + 1, tau * x[0] ** 2 + x[0] - 1])
+
+    def pjac(x, tau):
+        return np.array([[1], [2 * tau * x[0] + 1]])
+
+    def no_step_length_control(res, x, res_ev, jac_ev, args, descent_direction, *_):
+        return 1, res(x + descent_direction, *args), 1
+
+    gd = Golden("powell")
+    xs = []
+    out = g.gauss_newton(pres, np.array([1.0]), pjac, args=(-5,), max_iter=19, step_length_control=no_step_length_control,
+                         callback=lambda x, nfev, cg_iter: xs.append(float(np.asarray(x)[0])))
+    gr = gd.run("tau-5_no_step_length_control")
+    assert (out.nit, out.nrev, out.success) == (18, 19, False)
+    assert np.max(np.abs(np.array(xs) - gr["xs"][:, 0])) < 1e-12
+    with pytest.raises(g.StepLengthConvergenceError) as ei:
+        g.gauss_newton(pres, np.array([1.0]), pjac, args=(-5,), max_iter=19, callback=lambda **k: None)
+    assert "Norm of descent_direction" in ei.value.message
+    with pytest.raises(TypeError):
+        g.gauss_newton(pres, np.array([1.0]), pjac, args=(5,))       # default callback is called with keywords
+    with pytest.raises(ValueError):
+        g.gauss_newton_krylow(pres, np.zeros(1), pjac, args=(5,), callback=lambda **k: None)
+
+
+def test_flat_module_names(g):
+    import sys
+    g.install_flat_names()
+    import gauss_newton_krylow as m1
+    import krylow as m2
+    from bratu_pde_problem import BratuPdeProblem
+    from regression_result import RegressionResult
+    assert m1.gauss_newton_krylow is g.gauss_newton_krylow and m2.GeneralizedKrylowSubspace is g.GeneralizedKrylowSubspace
+    assert BratuPdeProblem is g.BratuPdeProblem
+    r = RegressionResult("gauss newton", np.ones(2), True, 3, 2, 2)
+    assert "converged successfuly" in str(r) and r.nrev == 3
+    for name in ("gauss_newton_krylow", "krylow", "bratu_pde_problem", "regression_result", "armijo_goldstein",
+                 "gauss_newton", "rosenbrock_problem", "benchmark"):
+        sys.modules.pop(name, None)
+
+
+def test_benchmark_harness(g):
+    from gauss_newton_via_generalized_krylov_subspaces_b200.benchmark import benchmark_method, reverse_accumulation
+    assert reverse_accumulation([2, 3, 7]) == [2, 1, 4] and reverse_accumulation([]) == []
+    gd = Golden("bratu_g34")
+    pb = g.BratuPdeProblem(34, 5, 10)
+    res, jac, err = pb.make_res(gd["y"]), pb.make_jac(), pb.make_error()
+    e, l, nf, cg = benchmark_method(g.gauss_newton_krylow, res, gd["u0"], jac, err, kwargs=dict(max_iter=6))
+    gr = gd.run("gnk_res_old")
+    assert len(e) == 6 and nf == [2, 1, 1, 1, 1] and cg == []
+    assert np.allclose(e[1:], gr["err"][:5], rtol=1e-10) and np.allclose(l[1:], gr["loss"][:5], rtol=1e-10)
