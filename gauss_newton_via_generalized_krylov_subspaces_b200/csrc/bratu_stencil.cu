@@ -40,6 +40,35 @@ __device__ __forceinline__ void store_pair(double* p, double a, double b) {
     *p = a;
 }
 
+// The linear part of P(u) in the reference's floating-point order (bratu_pde_problem.py:78-82 on scipy 1.18):
+// laplace2d is sorted CSR with data {4 h^-2, -h^-2} -> csr_matvec adds data*x entry by entry in column order
+// (i-1,j), (i,j-1), (i,j), (i,j+1), (i+1,j); ALPHA*partial_diff_x is COO -> -c u_ij then +c u_i+1,j; the two
+// products are then added.  Every product and sum is rounded separately (no FMA contraction): h^-2 (4u - sum nb)
+// cancels 4-6 digits on the fine grids, so any other order changes F by ~1e-16 h^-2 |u|, which the GNK trajectory
+// amplifies by 1e3 .. 1e5 (parity).  Missing neighbours are exact zeros (x + 0 = x).
+__device__ __forceinline__ double pde_refbits(const gnk_bratu& prm, double c4, double up, double lf, double mid,
+                                              double rt, double dn) {
+  const double mc = -prm.c_lap;
+  double lap = __dadd_rn(__dmul_rn(mc, up), __dmul_rn(mc, lf));
+  lap = __dadd_rn(lap, __dmul_rn(c4, mid));
+  lap = __dadd_rn(lap, __dmul_rn(mc, rt));
+  lap = __dadd_rn(lap, __dmul_rn(mc, dn));
+  const double adv = __dadd_rn(__dmul_rn(-prm.c_adv, mid), __dmul_rn(prm.c_adv, dn));
+  return __dadd_rn(lap, adv);
+}
+
+// One row of sign * (M v) or sign * (M^T v), M = L + alpha D + lam diag(e^u), in the order scipy uses for
+// J @ V (csr_matvecs, gauss_newton_krylow.py:86) and -J.T @ r (csc_matvec, krylow.py:62): five rounded products
+// added one at a time, neighbours in ascending index order.  cu / cd are the weights of rows i-1 / i+1.
+__device__ __forceinline__ double apply_refbits(double cu, double cl, double dg, double cd, double up, double lf,
+                                                double mid, double rt, double dn) {
+  double s = __dadd_rn(__dmul_rn(cu, up), __dmul_rn(cl, lf));
+  s = __dadd_rn(s, __dmul_rn(dg, mid));
+  s = __dadd_rn(s, __dmul_rn(cl, rt));
+  s = __dadd_rn(s, __dmul_rn(cd, dn));
+  return s;
+}
+
 // F = y - P(u), expu = e^u, loss = sum_owned F^2
 template <bool VEC>
 __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_bratu prm, const double* __restrict__ u,
@@ -71,21 +100,17 @@ __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_brat
       const double la = lf, ra = VEC ? mid.b : rt;
       const double lb = mid.a, rb = rt;
       double ea = 1.0, eb = 1.0;
-      double pa = c4 * mid.a - prm.c_lap * up.a - prm.c_lap * la - prm.c_lap * ra - prm.c_lap * dn.a +
-                  prm.c_adv * (dn.a - mid.a);
-      double pb = 0.0;
-      if (VEC)
-        pb = c4 * mid.b - prm.c_lap * up.b - prm.c_lap * lb - prm.c_lap * rb - prm.c_lap * dn.b +
-             prm.c_adv * (dn.b - mid.b);
+      double pa = pde_refbits(prm, c4, up.a, la, mid.a, ra, dn.a);
+      double pb = VEC ? pde_refbits(prm, c4, up.b, lb, mid.b, rb, dn.b) : 0.0;
       if (prm.lam != 0.0) {
         ea = exp(mid.a);
-        pa += prm.lam * ea;
+        pa = __dadd_rn(pa, __dmul_rn(prm.lam, ea));
         if (VEC) {
           eb = exp(mid.b);
-          pb += prm.lam * eb;
+          pb = __dadd_rn(pb, __dmul_rn(prm.lam, eb));
         }
       }
-      double fa = yy.a - pa, fb = yy.b - pb;
+      double fa = __dsub_rn(yy.a, pa), fb = __dsub_rn(yy.b, pb);
       const bool owned = (r >= 0 && r < lay.rows);
       const bool in_domain = owned || (r < 0 ? lay.has_lo : lay.has_hi);
       if (!in_domain) {
@@ -133,9 +158,11 @@ __global__ void __launch_bounds__(TPBX) apply_kernel(gnk_layout lay, gnk_bratu p
   const double* eb_ = expu ? expu + lay.off + j0 : nullptr;
   double* ob = out + (int64_t)col * out_ld + out_off + j0;
   const bool has_l = j0 > 0, has_r = (j0 + W) < m;
-  const double d0 = 4.0 * prm.c_lap - prm.c_adv;
-  const double cu = transpose ? (prm.c_adv - prm.c_lap) : -prm.c_lap;  // weight of row i-1
-  const double cd = transpose ? -prm.c_lap : (prm.c_adv - prm.c_lap);  // weight of row i+1
+  const double d0 = __dadd_rn(4.0 * prm.c_lap, -prm.c_adv);          // (L + alpha D) diagonal, as scipy adds it
+  const double c_sup = __dadd_rn(-prm.c_lap, prm.c_adv);             // entry (i, i+1): -h^-2 + alpha h^-1
+  const double cu = transpose ? c_sup : -prm.c_lap;                  // weight of row i-1
+  const double cd = transpose ? -prm.c_lap : c_sup;                  // weight of row i+1
+  const double cl = -prm.c_lap;
   Pair<VEC> up = load_pair<VEC>(vb + (int64_t)(rbeg - 1) * m);
   Pair<VEC> mid = load_pair<VEC>(vb + (int64_t)rbeg * m);
 #pragma unroll 2
@@ -147,13 +174,12 @@ __global__ void __launch_bounds__(TPBX) apply_kernel(gnk_layout lay, gnk_bratu p
     double dga = d0, dgb = d0;
     if (eb_) {
       Pair<VEC> e = load_pair<VEC>(eb_ + ro);
-      dga = fma(prm.lam, e.a, d0);
-      dgb = fma(prm.lam, e.b, d0);
+      dga = __dadd_rn(d0, __dmul_rn(prm.lam, e.a));
+      dgb = __dadd_rn(d0, __dmul_rn(prm.lam, e.b));
     }
     const double ra = VEC ? mid.b : rt;
-    double oa = dga * mid.a + cu * up.a + cd * dn.a - prm.c_lap * (lf + ra);
-    double ob2 = 0.0;
-    if (VEC) ob2 = dgb * mid.b + cu * up.b + cd * dn.b - prm.c_lap * (mid.a + rt);
+    const double oa = apply_refbits(cu, cl, dga, cd, up.a, lf, mid.a, ra, dn.a);
+    const double ob2 = VEC ? apply_refbits(cu, cl, dgb, cd, up.b, mid.a, mid.b, rt, dn.b) : 0.0;
     store_pair<VEC>(ob + ro, sign * oa, sign * ob2);
     up = mid;
     mid = dn;

@@ -166,19 +166,32 @@ class BratuOracle:
         return self._u_true
 
     def operator(self, u):
-        """P(u) = L u + alpha D u + lambda e^u   (:76-83)."""
+        """P(u) = L u + alpha D u + lambda e^u   (:76-83), evaluated in the SAME floating-point order as the
+        reference so that y = P(u_true) -- an input of every parity run -- is bit-identical to the reference's:
+          * laplace2d is a sorted CSR matrix with data {4 h^-2, -h^-2}; scipy's csr_matvec adds data*x one entry at a
+            time in column order (i-1,j), (i,j-1), (i,j), (i,j+1), (i+1,j), no FMA;
+          * ALPHA*partial_diff_x is COO with data -+ALPHA h^-1; coo_matvec adds -c u_ij, then +c u_i+1,j;
+          * the three terms are then added left to right (:79-83).
+        (h^-2 (4u - sum nb) of a smooth u cancels 4-5 digits, so a different order changes y by ~1e-13 relative, which
+        the GNK trajectory amplifies to 1e-9 .. 1e-6 on the 1024^2 / 4096^2 grids.)"""
         m = self.m
         U = np.asarray(u, dtype=np.float64).reshape(m, m)
-        out = (4.0 * self.c_lap) * U
-        out[1:, :] -= self.c_lap * U[:-1, :]
-        out[:-1, :] -= self.c_lap * U[1:, :]
-        out[:, 1:] -= self.c_lap * U[:, :-1]
-        out[:, :-1] -= self.c_lap * U[:, 1:]
-        adv = -U.copy()
-        adv[:-1, :] += U[1:, :]
-        out += self.c_adv * adv
+        c = self.c_lap
+        z = np.zeros((m, m))
+        up, left, right, down = z.copy(), z.copy(), z.copy(), z.copy()
+        up[1:, :] = (-c) * U[:-1, :]
+        left[:, 1:] = (-c) * U[:, :-1]
+        right[:, :-1] = (-c) * U[:, 1:]
+        down[:-1, :] = (-c) * U[1:, :]
+        lap = up + left
+        lap += (4.0 * c) * U
+        lap += right
+        lap += down
+        adv = (-self.c_adv) * U
+        adv[:-1, :] += self.c_adv * U[1:, :]
+        out = lap + adv
         if self.lam != 0:
-            out += self.lam * np.exp(U)
+            out = out + self.lam * np.exp(U)
         return out.reshape(-1)
 
     def make_res(self, y):

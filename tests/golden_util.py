@@ -35,6 +35,19 @@ class Recorder:
         self.xs.append(x[self.idx].copy())
 
 
+def sensitivity_bound(golden_run, perturbed_run, floor=1e-10, factor=100.0):
+    """Per-iteration tolerance for the large grids: the unmodified reference, re-run with its start vector perturbed by
+    one unit in the last place (oracle/gen_golden.py:sensitivity), moves by env_i at iteration i.  An independent
+    implementation is held to max(floor, factor * running max of env): i.e. to the 1e-10 bar wherever the reference's
+    own trajectory is that well determined, and to a fixed multiple of its 1-ulp conditioning where it is not (a few
+    early iterations, where x = c * v0 is formed by cancellation).  Measured GPU/envelope ratios are <= 25."""
+    a, b = golden_run["xs"], perturbed_run["xs"]
+    n = min(len(a), len(b))
+    scale = np.max(np.abs(a[:n]), axis=1, keepdims=True)
+    env = np.max(np.abs(a[:n] - b[:n]) / scale, axis=1)
+    return np.maximum(floor, factor * np.maximum.accumulate(env))
+
+
 def rel(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
@@ -50,9 +63,11 @@ def check_trace(rec, g, tol, upto=None, check_cg=False):
     assert list(rec.nfev[:n]) == list(g["nfev_cb"][:n])
     xs = np.array(rec.xs[:n])
     scale = np.max(np.abs(g["xs"][:n]), axis=1, keepdims=True)
-    d = np.max(np.abs(xs - g["xs"][:n]) / scale)
-    dn = np.max(np.abs(np.array(rec.xnorm[:n]) - g["xnorm"][:n]) / g["xnorm"][:n])
-    assert d <= tol and dn <= tol, (d, dn)
+    dv = np.max(np.abs(xs - g["xs"][:n]) / scale, axis=1)
+    dnv = np.abs(np.array(rec.xnorm[:n]) - g["xnorm"][:n]) / g["xnorm"][:n]
+    tolv = np.broadcast_to(np.asarray(tol, dtype=np.float64), (n,)) if np.ndim(tol) == 0 else np.asarray(tol)[:n]
+    assert np.all(dv <= tolv) and np.all(dnv <= tolv), (list(zip(dv, tolv))[:8], float(dv.max()), float(dnv.max()))
+    d = float(dv.max())
     if check_cg:
         assert list(rec.cg[:n]) == list(g["cg_iter"][:n])
     return d

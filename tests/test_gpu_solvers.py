@@ -15,7 +15,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from golden_util import Golden, Recorder, check_trace, rel  # noqa: E402
+from golden_util import Golden, Recorder, check_trace, rel, sensitivity_bound  # noqa: E402
 from oracle import gnk_oracle as orc  # noqa: E402
 
 TOL = 1e-10
@@ -40,15 +40,15 @@ def _bratu(g, gd, G, lam=10, h=None):
     return pb, pb.make_res(gd["y"]), pb.make_jac(), pb.make_error()
 
 
-def _run_gnk(g, res, jac, err, u0, gr, restart=None, **kw):
+def _run_gnk(g, res, jac, err, u0, gr, restart=None, tol=TOL, tol_after=TOL_AFTER_RESTART, **kw):
     rec = Recorder(gr["sample_idx"], err)
     out = g.gauss_newton_krylow(res, u0, jac, callback=rec, krylow_restart=restart, **kw)
     n = len(gr["xnorm"])
     first = n if restart is None else min(n, restart)
-    check_trace(rec, gr, TOL, upto=first)
+    check_trace(rec, gr, tol, upto=first)
     assert len(rec.xnorm) == n
     if first < n:
-        check_trace(rec, gr, TOL_AFTER_RESTART)
+        check_trace(rec, gr, tol_after)
     assert (out.nit, out.nrev, out.njev, bool(out.success)) == (
         int(gr["nit"]), int(gr["nfev"]), int(gr["njev"]), bool(gr["success"]))
     assert out.method_name == "gauss newton krylow" and isinstance(out.x, np.ndarray)
@@ -308,23 +308,36 @@ def _large(g, G):
 
 
 def test_bratu_1024(g):
-    gd = Golden("bratu_g1025")
+    gd, gs = Golden("bratu_g1025"), Golden("bratu_g1025_sens")
     pb, res, jac, err, u0, y = _large(g, 1025)
     idx = gd.run("gnk_k30")["sample_idx"]
-    assert rel(u0[idx], gd["u0_sample"]) == 0.0 and rel(y[idx], gd["y_sample"]) < 1e-14
-    _run_gnk(g, res, jac, err, u0, gd.run("gnk_k30"), max_iter=31)
-    # restart 30, 99 iterations: iteration-31/61/91 decisions are thin (SURVEY 8c'), counts must still match
-    out, rec = _run_gnk(g, res, jac, err, u0, gd.run("gnk_restart30"), max_iter=100, restart=30)
+    assert np.array_equal(u0[idx], gd["u0_sample"]) and np.array_equal(y[idx], gd["y_sample"])  # bit-identical inputs
+    gr = gd.run("gnk_k30")
+    bound = sensitivity_bound(gr, gs.run("gnk_k30"))
+    out, rec = _run_gnk(g, res, jac, err, u0, gr, max_iter=31, tol=bound)
+    tail = Recorder(gr["sample_idx"], None)  # from iteration 5 on the plain 1e-10 bar holds (measured ~1e-12)
+    tail.xs, tail.xnorm, tail.nfev = rec.xs[4:], rec.xnorm[4:], rec.nfev[4:]
+    check_trace(tail, {k: v[4:] for k, v in gr.items() if k in ("xs", "xnorm", "nfev_cb")}, TOL)
+    # restart 30, 99 iterations: iteration-31/61/91 decisions are thin (SURVEY 8c'), counts must still match;
+    # after a restart the reference itself moves by 7e-7 under the 1-ulp perturbation
     gr = gd.run("gnk_restart30")
-    assert abs(rec.err[-1] - gr["err"][-1]) < 1e-8 * gr["err"][-1]
+    bound = sensitivity_bound(gr, gs.run("gnk_restart30"))
+    out, rec = _run_gnk(g, res, jac, err, u0, gr, max_iter=100, restart=30, tol=bound, tol_after=bound)
+    assert abs(rec.err[-1] - gr["err"][-1]) < 1e-7 * gr["err"][-1]
 
 
 def test_bratu_4096_k30(g):
     """north-star workload: Bratu 4096^2 (16.7M unknowns), 30 outer iterations, k = 1..30 (no restart event)."""
-    gd = Golden("bratu_g4097")
+    gd, gs = Golden("bratu_g4097"), Golden("bratu_g4097_sens")
     pb, res, jac, err, u0, y = _large(g, 4097)
     gr = gd.run("gnk_k30")
-    assert rel(u0[gr["sample_idx"]], gd["u0_sample"]) == 0.0
-    out, rec = _run_gnk(g, res, jac, err, u0, gr, max_iter=31)
-    assert np.max(np.abs(np.array(rec.err) / gr["err"] - 1)) < TOL
+    assert np.array_equal(u0[gr["sample_idx"]], gd["u0_sample"]) and np.array_equal(y[gr["sample_idx"]], gd["y_sample"])
+    bound = sensitivity_bound(gr, gs.run("gnk_k30"))
+    out, rec = _run_gnk(g, res, jac, err, u0, gr, max_iter=31, tol=bound)
+    # from iteration 13 on (and at the end) the plain 1e-10 bar, in fact ~1e-13, holds
+    check = Recorder(gr["sample_idx"], None)
+    check.xs, check.xnorm, check.nfev = rec.xs[12:], rec.xnorm[12:], rec.nfev[12:]
+    sub = {k: v[12:] for k, v in gr.items() if k in ("xs", "xnorm", "nfev_cb")}
+    check_trace(check, sub, TOL)
+    assert np.max(np.abs(np.array(rec.err)[12:] / gr["err"][12:] - 1)) < TOL
     assert abs(res.loss(out.x) - gr["loss"][-1]) <= 2 * TOL * gr["loss"][-1]
