@@ -1,0 +1,81 @@
+"""torchrun worker for the N>1 CUDA+NCCL path (launched by tests/test_gpu_multi.py or by hand):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_worker.py
+
+One rank per GPU; every rank builds the same problem, owns a slab of grid rows, and the solver exchanges one
+2-row halo per outer iteration plus a few tiny all-gathers (NCCL owned by libgnk_b200.so).  Rank 0 checks the
+result against the reference's golden traces; all ranks must hold bit-identical global results.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import gauss_newton_via_generalized_krylov_subspaces_b200 as g
+    from golden_util import Golden, Recorder, check_trace, rel, sensitivity_bound
+    from oracle import gnk_oracle as orc
+
+    rt = g.get_runtime()
+    assert rt.world == world and rt.lib.gnk_comm_size(rt.ctx) == world
+
+    def gather_equal(x):
+        t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        ts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(ts, t)
+        return all(torch.equal(ts[0], u) for u in ts[1:])
+
+    # ---- small, uneven slabs, odd row length, restarts ------------------------------------------
+    gd = Golden("bratu_g34")
+    pb = g.BratuPdeProblem(34, 5, 10)
+    assert rel(pb.pde_operator(pb.u_true), gd["y"]) < 1e-14
+    res, jac, err = pb.make_res(gd["y"]), pb.make_jac(), pb.make_error()
+    o = orc.BratuOracle(34, 5, 10)
+    v = np.random.RandomState(0).normal(size=o.n)
+    J, Jo = jac(gd["u0"]), o.make_jac()(gd["u0"])
+    assert rel(J @ v, Jo @ v) < 1e-14 and rel(J.T @ v, Jo.T @ v) < 1e-14
+    gr = gd.run("gnk_res_old")
+    rec = Recorder(gr["sample_idx"], err)
+    out = g.gauss_newton_krylow(res, gd["u0"], jac, callback=rec, krylow_restart=12, max_iter=40)
+    check_trace(rec, gr, 1e-10, upto=12)
+    check_trace(rec, gr, 1e-8)
+    assert (out.nit, out.nrev, out.njev) == (int(gr["nit"]), int(gr["nfev"]), int(gr["njev"]))
+    assert gather_equal(out.x), "ranks disagree on the global result"
+    if rank == 0:
+        print(f"[multi] G=34 world={world}: nit={out.nit} ok", flush=True)
+
+    # ---- Bratu 1024^2, k <= 30: golden trace of the reference ----------------------------------------
+    gd, gs = Golden("bratu_g1025"), Golden("bratu_g1025_sens")
+    o = orc.BratuOracle(1025, 5, 10)
+    y, u0 = o.operator(o.u_true), o.start_vector(seed=42)
+    pb = g.BratuPdeProblem(1025, 5, 10)
+    res, jac, err = pb.make_res(y), pb.make_jac(), pb.make_error()
+    gr = gd.run("gnk_k30")
+    rec = Recorder(gr["sample_idx"], err)
+    out = g.gauss_newton_krylow(res, u0, jac, callback=rec, max_iter=31)
+    check_trace(rec, gr, sensitivity_bound(gr, gs.run("gnk_k30")))
+    assert (out.nit, out.nrev) == (30, 31) and gather_equal(out.x)
+    if rank == 0:
+        xs = np.array(rec.xs)
+        d = np.max(np.abs(xs - gr["xs"]) / np.max(np.abs(gr["xs"]), axis=1, keepdims=True), axis=1)
+        print(f"[multi] G=1025 world={world}: nit={out.nit} max dev {d.max():.2e} tail dev {d[4:].max():.2e} ok", flush=True)
+        print("MULTI_OK", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
