@@ -18,6 +18,7 @@ box) on the host cores on the same workload, each step a bounded sample of it.
 Multi-GPU (torchrun, one rank per GPU): the grid rows are partitioned into slabs, scaling is strong.
 """
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -268,7 +269,18 @@ def run_ours(a):
 
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # the contract is ONE JSON line on stdout: the solvers' own prints (the reference's "reached maximal iteration
+    # bound" warning etc.) go to stderr
+    real_stdout = sys.stdout
+    with contextlib.redirect_stdout(sys.stderr):
+        _emit = print
+
+        def print(*a, **k):  # noqa: A001  (the JSON line)
+            k.setdefault("file", real_stdout)
+            _emit(*a, **k)
+
+        globals()["print"] = print
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
