@@ -228,12 +228,14 @@ def run_ours(a):
             o = g.gauss_newton_krylow(r, u0_pin.numpy(), j, **kw)
             return o
 
-        for _ in range(max(1, a.warmup - 1)):
-            step_e2e()
+        o = None
+        for _ in range(a.warmup):
+            o = step_e2e()
         barrier()
         t0 = time.perf_counter()
         its_e = 0
         for _ in range(a.steps):
+            del o  # give the previous result's pinned buffer back before the next solve allocates its own
             o = step_e2e()
             its_e += o.nit
         barrier()
