@@ -47,6 +47,71 @@ def tsqr_solve(rt, A, lda, n_rows, k, y, sign, out):
                "gnk_tsqr_ls")
 
 
+def cgls_dense(rt, JV, ldjv, n_rows, k, y, sign, rtol, out):
+    """Projected least squares by CGLS instead of QR (BASELINE config 5: "Krylov dim 50 with CGLS inner solve"):
+    min || sign*JV d - y || via CG on the normal equations with the Jacobi preconditioner 1/diag(A^T A), i.e. the
+    reference's ``cg_least_squares(A, y, cg_rtol, preconditioner=True)`` (gauss_newton.py:11-60 / scipy cg) applied to
+    the dense n x k matrix A = sign*JV.  The n-sized work (A p = JV p, A^T t = JV^T t, column norms) runs in the same
+    combine / dots / norm kernels as the Krylov path, row-sharded with one k-sized all-reduce per product; the
+    k-sized CG recurrences run on the host.  Fills ``out`` like ``gnk_tsqr_ls`` (d, ||JV d||^2, -, 0, ||d||^2).
+    Returns the number of CG iterations."""
+    lib = rt.lib
+    lay = make_layout(dict(flat_layout_fields(n_rows), ld=ldjv))
+    h = rt.zeros(_NB)
+    pdev = rt.zeros(_NB)
+    t = rt.empty(ldjv)
+    stats = rt.zeros(2 * k)
+    stage = rt.pinned(_NB)
+    stage_np = stage.numpy()
+
+    def at_times(vec):  # A^T vec = sign * JV^T vec
+        _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(lay), ptr(JV), k, ptr(vec), ptr(h), rt.stream), "gnk_cgs_dots")
+        rt.allreduce(h, k, 0)
+        return sign * rt.read(h, k)
+
+    def a_times(pv):  # t = JV pv (the sign is applied by the caller)
+        stage_np[:k] = pv
+        pdev[:k].copy_(stage[:k], non_blocking=True)
+        _lib.check(lib.gnk_combine(rt.ctx, C.byref(lay), ptr(JV), k, ptr(pdev), None, 0.0, ptr(t), rt.stream),
+                   "gnk_combine")
+
+    for j in range(k):
+        _lib.check(lib.gnk_norm_stats(rt.ctx, C.byref(lay), ptr(JV, j * ldjv), ptr(stats, 2 * j), rt.stream),
+                   "gnk_norm_stats")
+    rt.allreduce(stats, 2 * k, 0)
+    minv = 1.0 / (sign * sign * rt.read(stats, 2 * k)[0::2])
+    b = at_times(y)
+    bn = float(np.linalg.norm(b))
+    x = np.zeros(k)
+    its = 0
+    if bn != 0.0:
+        atol = rtol * bn
+        r = b.copy()
+        rho_prev, pv = None, None
+        for it in range(10 * k):
+            if np.linalg.norm(r) < atol:
+                break
+            z = minv * r
+            rho = float(np.dot(r, z))
+            pv = z.copy() if it == 0 else z + (rho / rho_prev) * pv
+            a_times(pv)
+            q = sign * at_times(t)  # A^T (A p) = sign^2 JV^T JV p
+            alpha = rho / float(np.dot(pv, q))
+            x += alpha * pv
+            r -= alpha * q
+            rho_prev = rho
+            its += 1
+    a_times(x)
+    _lib.check(lib.gnk_norm_stats(rt.ctx, C.byref(lay), ptr(t), ptr(stats), rt.stream), "gnk_norm_stats")
+    rt.allreduce(stats, 1, 0)
+    g = float(rt.read(stats, 1)[0])
+    stage_np[:k] = x
+    stage_np[k:k + 4] = (g, 0.0, 0.0, float(np.dot(x, x)))
+    out[:k + 4].copy_(stage[:k + 4], non_blocking=True)
+    rt.sync()
+    return its
+
+
 def linear_least_squares(A, y):
     """Least squares solution of ||y - A x|| by Householder TSQR on the device (reference :16-36: economic QR,
     a print per |r_kk| <= 1e-8, triangular solve).  A: (n, k) ndarray, y: (n,) ndarray -> x: (k,) ndarray."""
@@ -82,6 +147,8 @@ def gauss_newton_krylow(
     version: str = "res_old",
     reorth_passes: int = 1,
     x_on_device: bool = False,
+    ls_solver: str = "qr",
+    cg_rtol: float = 1e-4,
 ) -> RegressionResult:
     """
     Parameters
@@ -96,6 +163,8 @@ def gauss_newton_krylow(
     callback: Called as callback(x=, nfev=, cg_iter=None) once per iteration; x converts lazily to ndarray.
     version: One of ['res_old','res_new','jac_old_res_old','jac_old_res_new'] (see reference :61).
     reorth_passes: 1 = the reference's single classical Gram-Schmidt pass (krylow.py:64); 2 = CGS2.
+    ls_solver: "qr" = Householder TSQR (the reference's QR); "cgls" = Jacobi-preconditioned CG on the normal equations
+        of the projected problem with tolerance ``cg_rtol`` (BASELINE config 5).
     x_on_device: leave the solution in HBM (RegressionResult.x is then a lazy DeviceVector).  x0 may likewise be a
         DeviceVector made by ``BratuPdeProblem.dev.resident(u0)``.
 
@@ -172,8 +241,13 @@ def gauss_newton_krylow(
         # projected operator and projected least squares  (:86-89)
         with rt.mark("spmm", 8.0 * n_res_own * (2 * k + 1)):
             jac_ev.matmat(krylow.V, ld, k, JV, ldjv)
-        with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
-            tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk)
+        if ls_solver == "qr":
+            with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
+                tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk)
+        elif ls_solver == "cgls":
+            cgls_dense(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, cg_rtol, blk)
+        else:
+            raise ValueError("ls_solver must be 'qr' or 'cgls'")
         _lib.check(lib.gnk_dot(rt.ctx, k, ptr(c), ptr(c), ptr(blk, _SC_CPREV), rt.stream), "gnk_dot")
 
         # Armijo-Goldstein in coordinate space  (:91-93)

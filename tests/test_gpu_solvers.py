@@ -341,3 +341,29 @@ def test_bratu_4096_k30(g):
     check_trace(check, sub, TOL)
     assert np.max(np.abs(np.array(rec.err)[12:] / gr["err"][12:] - 1)) < TOL
     assert abs(res.loss(out.x) - gr["loss"][-1]) <= 2 * TOL * gr["loss"][-1]
+
+
+def test_gnk_with_cgls_inner_solve(g):
+    """BASELINE config 5 at CPU-checkable size: GNK with krylow_restart=50 whose projected least squares is solved by
+    CGLS on the device.  The reference never runs this combination; the oracle is the reference's cg_least_squares
+    patched in for linear_least_squares (with cg_rtol=1e-10 it reproduces the QR run)."""
+    gd = Golden("bratu_g101")
+    pb, res, jac, err = _bratu(g, gd, 101)
+    o = orc.BratuOracle(101, 5, 10)
+    its = []
+
+    def ls(A, y, log):
+        x, n = orc.cgls(A, y, rtol=1e-10, preconditioner=True)
+        its.append(n)
+        return x
+
+    ref = orc.gnk(o.make_res(gd["y"]), gd["u0"], o.make_jac(), restart=50, max_iter=61, ls=ls)
+    out = g.gauss_newton_krylow(res, gd["u0"], jac, krylow_restart=50, max_iter=61, callback=lambda **k: None,
+                                ls_solver="cgls", cg_rtol=1e-10)
+    assert (out.nit, out.nrev, out.njev, out.success) == (ref["nit"], ref["nfev"], ref["njev"], ref["success"])
+    assert rel(out.x, ref["x"]) < 1e-6 and max(its) <= 60
+    qr = g.gauss_newton_krylow(res, gd["u0"], jac, krylow_restart=50, max_iter=61, callback=lambda **k: None)
+    assert rel(out.x, qr.x) < 1e-6
+    loose = g.gauss_newton_krylow(res, gd["u0"], jac, krylow_restart=50, max_iter=61, callback=lambda **k: None,
+                                  ls_solver="cgls", cg_rtol=1e-4)
+    assert abs(err(loose.x) - err(qr.x)) < 1e-3 * err(qr.x)

@@ -189,3 +189,44 @@ def test_benchmark_harness(g):
     gr = gd.run("gnk_res_old")
     assert len(e) == 6 and nf == [2, 1, 1, 1, 1] and cg == []
     assert np.allclose(e[1:], gr["err"][:5], rtol=1e-10) and np.allclose(l[1:], gr["loss"][:5], rtol=1e-10)
+
+
+def test_host_gnk_with_cgls_inner_solve(g):
+    """BASELINE config 5 at toy size: GNK whose projected least squares is solved by CGLS (the reference never runs
+    this combination; the oracle is the reference's cg_least_squares patched in for linear_least_squares)."""
+    from oracle import gnk_oracle as orc
+    gd = Golden("bratu_g34")
+    pb = g.BratuPdeProblem(34, 5, 10)
+    res, jac, err = pb.make_res(gd["y"]), pb.make_jac(), pb.make_error()
+    o = orc.BratuOracle(34, 5, 10)
+    ls = lambda A, y, log: orc.cgls(A, y, rtol=1e-10, preconditioner=True)[0]  # noqa: E731
+    ref = orc.gnk(o.make_res(gd["y"]), gd["u0"], o.make_jac(), restart=20, max_iter=31, ls=ls)
+    out = g.gauss_newton_krylow(res, gd["u0"], jac, krylow_restart=20, max_iter=31, callback=lambda **k: None,
+                                ls_solver="cgls", cg_rtol=1e-10)
+    assert (out.nit, out.nrev, out.njev) == (ref["nit"], ref["nfev"], ref["njev"])
+    assert rel(out.x, ref["x"]) < 1e-6
+    qr = g.gauss_newton_krylow(res, gd["u0"], jac, krylow_restart=20, max_iter=31, callback=lambda **k: None)
+    assert rel(out.x, qr.x) < 1e-6   # tight CG tolerance reproduces the QR solve
+    with pytest.raises(ValueError):
+        g.gauss_newton_krylow(res, gd["u0"], jac, max_iter=3, callback=lambda **k: None, ls_solver="nope")
+
+
+def test_device_side_error_and_loss_in_callbacks(g):
+    """error(x) / loss(x) of the benchmark harness evaluated on the callback's DeviceVector in place."""
+    gd = Golden("bratu_g34")
+    pb = g.BratuPdeProblem(34, 5, 10)
+    res, jac, err = pb.make_res(gd["y"]), pb.make_jac(), pb.make_error()
+    seen = []
+
+    def cb(x, nfev, cg_iter):
+        assert isinstance(x, g.DeviceVector) and x._t is not None
+        e_dev, l_dev = err(x), res.loss(x)
+        assert x._host is None                      # nothing was copied to the host for that
+        xh = np.asarray(x)
+        seen.append((e_dev, np.linalg.norm(pb.u_true - xh), l_dev, 0.5 * np.sum(res(xh) ** 2)))
+
+    g.gauss_newton_krylow(res, gd["u0"], jac, callback=cb, max_iter=6)
+    a = np.array(seen)
+    gr = gd.run("gnk_res_old")
+    assert np.allclose(a[:, 0], a[:, 1], rtol=1e-13) and np.allclose(a[:, 2], a[:, 3], rtol=1e-12)
+    assert np.allclose(a[:, 0], gr["err"][:5], rtol=1e-10) and np.allclose(a[:, 2], gr["loss"][:5], rtol=1e-10)
