@@ -57,18 +57,6 @@ __device__ __forceinline__ double pde_refbits(const gnk_bratu& prm, double c4, d
   return __dadd_rn(lap, adv);
 }
 
-// One row of sign * (M v) or sign * (M^T v), M = L + alpha D + lam diag(e^u), in the order scipy uses for
-// J @ V (csr_matvecs, gauss_newton_krylow.py:86) and -J.T @ r (csc_matvec, krylow.py:62): five rounded products
-// added one at a time, neighbours in ascending index order.  cu / cd are the weights of rows i-1 / i+1.
-__device__ __forceinline__ double apply_refbits(double cu, double cl, double dg, double cd, double up, double lf,
-                                                double mid, double rt, double dn) {
-  double s = __dadd_rn(__dmul_rn(cu, up), __dmul_rn(cl, lf));
-  s = __dadd_rn(s, __dmul_rn(dg, mid));
-  s = __dadd_rn(s, __dmul_rn(cl, rt));
-  s = __dadd_rn(s, __dmul_rn(cd, dn));
-  return s;
-}
-
 // F = y - P(u), expu = e^u, loss = sum_owned F^2
 template <bool VEC>
 __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_bratu prm, const double* __restrict__ u,

@@ -128,4 +128,16 @@ __device__ __forceinline__ unsigned int linear_block_id() {
 }
 __device__ __forceinline__ unsigned int total_blocks() { return gridDim.x * gridDim.y * gridDim.z; }
 
+// One row of sign * (M v) or sign * (M^T v), M = L + alpha D + lam diag(e^u), in the order scipy uses for
+// J @ V (csr_matvecs, gauss_newton_krylow.py:86) and -J.T @ r (csc_matvec, krylow.py:62): five rounded products
+// added one at a time, neighbours in ascending index order.  cu / cd are the weights of rows i-1 / i+1.
+__device__ __forceinline__ double apply_refbits(double cu, double cl, double dg, double cd, double up, double lf,
+                                                double mid, double rt, double dn) {
+  double s = __dadd_rn(__dmul_rn(cu, up), __dmul_rn(cl, lf));
+  s = __dadd_rn(s, __dmul_rn(dg, mid));
+  s = __dadd_rn(s, __dmul_rn(cl, rt));
+  s = __dadd_rn(s, __dmul_rn(cd, dn));
+  return s;
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -16,6 +16,7 @@ and the host reads one small block of scalars per Armijo trial plus the breakdow
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Callable, Optional, Tuple
 
 import numpy as np
@@ -231,17 +232,28 @@ def gauss_newton_krylow(
 
     JV = None
     jv_cap = 0
+    # GNK_FUSED_LS=1 forms J V_k inside the TSQR leaf (saves the n x k buffer and its 16nk bytes of traffic); measured
+    # 14 % slower than SpMM + TSQR at 4096^2 because the leaf is issue-bound, so it is opt-in
+    fuse_ls = is_bratu and os.environ.get("GNK_FUSED_LS", "0") == "1"
     state = {}
 
     for iter in range(1, max_iter):
         k = krylow.k
-        if k > jv_cap:
+        # Bratu + QR: J V_k is formed inside the TSQR leaf and never stored (gnk_tsqr_ls_stencil, k <= 31)
+        fused = (fuse_ls and ls_solver == "qr" and k <= 31 and not jac_ev.transposed and jac_ev.scale == 1.0)
+        if not fused and k > jv_cap:
             jv_cap = min(MAX_COLUMNS, max(krylow.cap, k))
             JV = rt.empty(jv_cap * ldjv)
         # projected operator and projected least squares  (:86-89)
-        with rt.mark("spmm", 8.0 * n_res_own * (2 * k + 1)):
-            jac_ev.matmat(krylow.V, ld, k, JV, ldjv)
-        if ls_solver == "qr":
+        if fused:
+            with rt.mark("spmm+tsqr", 8.0 * n_res_own * (k + 2)):
+                prob.d.tsqr_fused(jac_ev.expu, krylow.V, ld, k, F_cur, -1.0, blk)
+        else:
+            with rt.mark("spmm", 8.0 * n_res_own * (2 * k + 1)):
+                jac_ev.matmat(krylow.V, ld, k, JV, ldjv)
+        if fused:
+            pass
+        elif ls_solver == "qr":
             with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
                 tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk)
         elif ls_solver == "cgls":

@@ -118,6 +118,14 @@ int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k
 int gnk_tsqr_ls(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k,
                 const double* d_y, double sign_a, double* d_out, void* stream);
 
+/* Fused form of gnk_stencil_apply + gnk_tsqr_ls for the Bratu stencil: the panel [sign_a * (J V_k) | r] is formed on
+ * the fly from the basis columns inside the TSQR leaf (tiles are 8 x 32 blocks of the grid staged with a one-cell
+ * halo), so J V_k (gauss_newton_krylow.py:86) is never written to or re-read from HBM.  d_V: k stored columns
+ * (stride ldv, halo rows valid); d_r: the residual as a stored column; d_out as gnk_tsqr_ls.  k <= 31. */
+int gnk_tsqr_ls_stencil(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
+                        const double* d_V, int64_t ldv, int k, const double* d_r, double sign_a,
+                        double* d_out, void* stream);
+
 /* ---- generic sparse Jacobians (rosenbrock_problem.py:14-19, foreign callables) ----------------- */
 /* out[:, j] = sign * A * in[:, j] for a CSR matrix with n_rows rows; in columns start at
  * d_in + j*in_ld + in_off, out columns at d_out + j*out_ld + out_off.  The transpose product is the

@@ -201,6 +201,15 @@ class MockLib:
         o[k + 4:2 * k + 4] = np.diag(R)[:k]
         return 0
 
+    def gnk_tsqr_ls_stencil(self, ctx, lay, prm, expu, V, ldv, k, r, sign_a, out, stream):
+        lay_o = obj(lay)
+        n = lay_o.n_own
+        JV = np.zeros(k * n)
+        self.gnk_stencil_apply(ctx, lay, prm, expu, V, ldv, k, -1.0, 0, C.c_void_p(JV.ctypes.data), n, 0, stream)
+        rv = arr(r, lay_o.ld)[lay_o.off:lay_o.off + n].copy()
+        return self.gnk_tsqr_ls(ctx, C.c_void_p(JV.ctypes.data), n, n, k, C.c_void_p(rv.ctypes.data), sign_a, out,
+                                stream)
+
     # ---- CSR ----
     def gnk_spmm_csr(self, ctx, n_rows, rowptr, col, val, inp, in_ld, in_off, k, sign, out, out_ld, out_off, stream):
         import scipy.sparse as sp

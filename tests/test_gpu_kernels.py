@@ -352,3 +352,36 @@ def test_armijo_goldstein_public_api(g):
     assert (s, it) == (so, ito) and np.array_equal(rn, rno)
     with pytest.raises(g.StepLengthConvergenceError):
         g.armijo_goldstein(res, x, r, J, (5,), -d)
+
+
+@pytest.mark.parametrize("G,k", [(12, 1), (12, 5), (35, 8), (34, 15), (130, 7), (131, 20), (258, 31), (1030, 12)])
+def test_fused_stencil_tsqr_matches_unfused(g, G, k):
+    """gnk_tsqr_ls_stencil (J V_k formed inside the TSQR leaf) against gnk_stencil_apply + gnk_tsqr_ls."""
+    _lib, device = _lib_mods()
+    from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve
+    pb = g.BratuPdeProblem(G, 5, 10)
+    d = pb.dev
+    rt = d.rt
+    n, ld, off = d.fields["n_own"], d.ld, d.fields["off"]
+    rs = np.random.RandomState(G * 100 + k)
+    V = rt.zeros(k * ld)
+    for j in range(k):
+        d.upload_x(rs.normal(size=pb.n), V[j * ld:(j + 1) * ld])
+    u, r = d.new_col(), d.new_col()
+    d.upload_x(0.3 * rs.normal(size=pb.n), u)
+    d.upload_x(rs.normal(size=pb.n), r)
+    E = d.new_col()
+    d.residual_into(u, d.zero_col(), d.new_col(), E, d.scal_tmp, depth=0)
+    ldjv = (n + 15) // 16 * 16
+    JV = rt.zeros(k * ldjv)
+    d.apply(E, V, ld, k, -1.0, 0, JV, ldjv, 0)
+    a, b = rt.zeros(256), rt.zeros(256)
+    tsqr_solve(rt, JV, ldjv, n, k, r[off:], -1.0, a)
+    d.tsqr_fused(E, V, ld, k, r, -1.0, b)
+    va, vb = rt.read(a, 2 * k + 4), rt.read(b, 2 * k + 4)
+    JVh = rt.download(JV).reshape(k, ldjv)[:, :n].T
+    dref = np.linalg.lstsq(-JVh, rt.download(r[off:off + n]), rcond=None)[0]
+    cond = np.linalg.cond(JVh)
+    assert rel(vb[:k], dref) < 1e-13 * max(cond, 10.0) and rel(va[:k], dref) < 1e-13 * max(cond, 10.0)
+    assert np.allclose(vb[k:k + 4], va[k:k + 4], rtol=1e-11, atol=0)           # |Rd|^2, resid^2, ndef, |d|^2
+    assert np.allclose(np.abs(vb[k + 4:]), np.abs(va[k + 4:]), rtol=1e-11)       # |diag R|
