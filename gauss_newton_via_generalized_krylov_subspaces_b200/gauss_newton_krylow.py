@@ -48,6 +48,16 @@ def tsqr_solve(rt, A, lda, n_rows, k, y, sign, out):
                "gnk_tsqr_ls")
 
 
+def _report_rank(vals, k):
+    """the prints of gauss_newton_krylow.py:32-34, and scipy's solve_triangular error for an exactly singular R (:35)"""
+    for _ in range(int(vals[k + 2])):
+        print("A is rank deficient")
+    diag = vals[k + 4:2 * k + 4]
+    zero = np.nonzero(diag == 0.0)[0]
+    if zero.size:
+        raise np.linalg.LinAlgError(f"singular matrix: resolution failed at diagonal {int(zero[0])}")
+
+
 def cgls_dense(rt, JV, ldjv, n_rows, k, y, sign, rtol, out):
     """Projected least squares by CGLS instead of QR (BASELINE config 5: "Krylov dim 50 with CGLS inner solve"):
     min || sign*JV d - y || via CG on the normal equations with the Jacobi preconditioner 1/diag(A^T A), i.e. the
@@ -131,8 +141,7 @@ def linear_least_squares(A, y):
     out = rt.zeros(2 * _NB + 8)
     tsqr_solve(rt, dA, lda, n, k, dy, 1.0, out)
     vals = rt.read(out, 2 * k + 4)
-    for _ in range(int(vals[k + 2])):
-        print("A is rank deficient")
+    _report_rank(vals, k)
     return vals[:k].copy()
 
 
@@ -274,8 +283,8 @@ def gauss_newton_krylow(
             trial_loss, prev_loss, lambda: float(state["vals"][k]), lambda: float(np.sqrt(state["vals"][k + 3])))
         nfev += nfev_delta
         vals = state["vals"]
-        for _ in range(int(vals[k + 2])):
-            print("A is rank deficient")
+        if ls_solver == "qr":
+            _report_rank(vals, k)
         squared_sum_d = float(vals[k + 3])
         squared_sum_x_prev = float(vals[_SC_CPREV])
 

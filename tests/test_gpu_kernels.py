@@ -385,3 +385,24 @@ def test_fused_stencil_tsqr_matches_unfused(g, G, k):
     assert rel(vb[:k], dref) < 1e-13 * max(cond, 10.0) and rel(va[:k], dref) < 1e-13 * max(cond, 10.0)
     assert np.allclose(vb[k:k + 4], va[k:k + 4], rtol=1e-11, atol=0)           # |Rd|^2, resid^2, ndef, |d|^2
     assert np.allclose(np.abs(vb[k + 4:]), np.abs(va[k + 4:]), rtol=1e-11)       # |diag R|
+
+
+def test_tsqr_degenerate_inputs(g, capsys):
+    """zero column -> scipy's solve_triangular error; all-zero right-hand side -> d = 0; single row; k at the limit."""
+    rs = np.random.RandomState(11)
+    A = rs.normal(size=(3000, 5))
+    y = rs.normal(size=3000)
+    A0 = A.copy()
+    A0[:, 2] = 0.0
+    with pytest.raises(np.linalg.LinAlgError):
+        g.linear_least_squares(A0, y)
+    assert "A is rank deficient" in capsys.readouterr().out
+    assert np.all(g.linear_least_squares(A, np.zeros(3000)) == 0.0)
+    x = g.linear_least_squares(np.array([[2.0]]), np.array([3.0]))
+    assert x.shape == (1,) and abs(x[0] - 1.5) < 1e-15
+    B = rs.normal(size=(104, 103))                       # square-ish, k = 103 = the panel limit
+    xb = g.linear_least_squares(B, rs.normal(size=104))
+    assert np.all(np.isfinite(xb))
+    from gauss_newton_via_generalized_krylov_subspaces_b200._lib import GnkError
+    with pytest.raises(GnkError):
+        g.linear_least_squares(rs.normal(size=(200, 104)), rs.normal(size=200))
