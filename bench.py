@@ -212,12 +212,27 @@ def run_ours(a):
         gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
         kernels[name] = dict(launches=p["launches"], ms=round(p["ms"], 3), achieved_gbs=round(gbs, 1),
                              frac=round(gbs / peak, 3), bytes_per_launch=p["bytes"] / max(p["launches"], 1))
+    # measured DRAM traffic per algorithmic byte from the committed ncu --set full captures (profiles/)
+    ncu_name = dict(tsqr="tsqr_kernel", spmm="apply_kernel", combine="combine_kernel", cgs_dots="dots_kernel",
+                    cgs_update="update_kernel", residual="residual_kernel")
+    try:
+        dram = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+    except Exception:
+        dram = {}
+    for name in kernels:
+        ratio = dram.get(ncu_name.get(name, ""), {}).get("ratio")
+        kernels[name]["traffic_per_launch"] = None if ratio is None else ratio * kernels[name]["bytes_per_launch"]
     top = max(prof, key=lambda k_: prof[k_]["ms"]) if prof else None
     roofline = None
     if top:
         roofline = dict(bound="hbm", kernel=top, achieved=kernels[top]["achieved_gbs"], peak=peak, unit="GB/s",
-                        frac=kernels[top]["frac"], traffic=None, peak_source=peak_src,
-                        share_of_step=round(prof[top]["ms"] / sum(p["ms"] for p in prof.values()), 3))
+                        frac=kernels[top]["frac"], traffic=kernels[top]["traffic_per_launch"], peak_source=peak_src,
+                        share_of_step=round(prof[top]["ms"] / sum(p["ms"] for p in prof.values()), 3),
+                        traffic_source="dram__bytes_read+write per algorithmic byte at k=30 (profiles/r01_dram_traffic.json)"
+                                       " x this run's bytes per launch",
+                        note="the TSQR leaf reads its panel exactly once but is FP64 issue/latency bound for k >~ 6 "
+                             "(DESIGN.md section 3); the streaming kernels are the HBM-bound ones, see `kernels`"
+                        if top == "tsqr" else None)
 
     # ---- end-to-end leg: host buffers in, host ndarray out ----------------------------------------
     e2e = None
