@@ -206,9 +206,32 @@ __global__ void __launch_bounds__(TPBX) normal_diag_kernel(gnk_layout lay, gnk_b
   }
 }
 
+// Rows per CTA strip.  A strip re-reads one halo row above and below (from L2), so taller is cheaper per row, but
+// the grid should fill whole waves of resident CTAs (8 x 128 threads per SM at <= 64 registers): a 1.7-wave grid
+// leaves a quarter of the machine idle in its second wave.  Pick the height with the best wave efficiency, charging
+// the halo re-reads lightly.
 inline int pick_tr(const gnk_ctx* ctx, int gx, int rows, int mult) {
+  const double cap = 8.0 * ctx->sm_count;
+  int best = 1;
+  double best_score = -1.0;
+  for (int tr = 32; tr >= 1; tr >>= 1) {
+    const double ctas = (double)gx * mult * (double)ceil_div(rows, tr);
+    const double waves = ctas / cap;
+    const double eff = (waves <= 1.0) ? waves : waves / (double)(int64_t)(waves + 0.999999);
+    const double score = eff - 0.05 * (2.0 / tr);
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = tr;
+    }
+  }
+  return best;
+}
+
+// the fused residual kernel carries exp() and a block reduction per strip: measured best with the tallest strip that
+// still gives every SM two CTAs
+inline int pick_tr_tall(const gnk_ctx* ctx, int gx, int rows) {
   int tr = 32;
-  while (tr > 1 && (int64_t)gx * mult * ceil_div(rows, tr) < 2LL * ctx->sm_count) tr >>= 1;
+  while (tr > 1 && (int64_t)gx * ceil_div(rows, tr) < 2LL * ctx->sm_count) tr >>= 1;
   return tr;
 }
 
@@ -232,7 +255,7 @@ int gnk_bratu_residual(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm
   const bool vec = (lay->m % 2) == 0;
   const int gx = (int)ceil_div(lay->m, (vec ? 2 : 1) * TPBX);
   const int R = lay->rows + 2 * depth;
-  const int tr = pick_tr(ctx, gx, R, 1);
+  const int tr = pick_tr_tall(ctx, gx, R);
   dim3 grid(gx, (unsigned)ceil_div(R, tr));
   GNK_REQUIRE((int64_t)grid.x * grid.y <= 65536, "gnk_bratu_residual: grid exceeds the partials scratch");
   double* part = ctx->d_partials + PART_RESID;

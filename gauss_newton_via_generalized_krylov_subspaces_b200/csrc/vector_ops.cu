@@ -115,45 +115,50 @@ __global__ void __launch_bounds__(TPB) normalize_kernel(const double* __restrict
 
 // ---------------------------------------------------------------------------------------------
 // h[j] = sum_i V[j*ld + i] * w[i], i in [0, n) (pointers already offset to the owned part)
-constexpr int JB = 16;
-__global__ void __launch_bounds__(TPB) dots_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
-                                                    const double* __restrict__ w, double* __restrict__ partials,
-                                                    unsigned int* ticket, double* __restrict__ h) {
-  __shared__ double sh[32];
+constexpr int JB = 8;  // columns per pass: 8 accumulators keep the kernel at ~64 registers -> 32+ warps per SM
+
+// one pass over NJ (compile-time) columns starting at Vb: every thread keeps NJ running sums
+template <int NJ>
+__device__ __forceinline__ void dots_pass(const double* __restrict__ Vb, int64_t ld, int64_t n,
+                                          const double* __restrict__ w, double (&acc)[JB]) {
   const int64_t nv = n >> 1;
   const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll 1
+  for (int64_t i = gt; i < nv; i += stride) {
+    const double2 wv = ld2(w + 2 * i);
+    double2 v[NJ];
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) v[u] = ld2_stream(Vb + (int64_t)u * ld + 2 * i);
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) acc[u] = fma(v[u].y, wv.y, fma(v[u].x, wv.x, acc[u]));
+  }
+  if ((n & 1) && gt == 0) {
+    const double wv = w[n - 1];
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) acc[u] = fma(Vb[(int64_t)u * ld + n - 1], wv, acc[u]);
+  }
+}
+
+__global__ void __launch_bounds__(TPB, 4) dots_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
+                                                    const double* __restrict__ w, double* __restrict__ partials,
+                                                    unsigned int* ticket, double* __restrict__ h) {
+  __shared__ double sh[32];
   for (int jb = 0; jb < k; jb += JB) {
     double acc[JB];
 #pragma unroll
     for (int u = 0; u < JB; ++u) acc[u] = 0.0;
     const int nj = min(JB, k - jb);
     const double* Vb = V + (int64_t)jb * ld;
-    if (nj == JB) {
-      for (int64_t i = gt; i < nv; i += stride) {
-        const double2 wv = ld2(w + 2 * i);
-        double2 v[JB];
-#pragma unroll
-        for (int u = 0; u < JB; ++u) v[u] = ld2_stream(Vb + (int64_t)u * ld + 2 * i);
-#pragma unroll
-        for (int u = 0; u < JB; ++u) acc[u] = fma(v[u].y, wv.y, fma(v[u].x, wv.x, acc[u]));
-      }
-    } else {
-      for (int64_t i = gt; i < nv; i += stride) {
-        const double2 wv = ld2(w + 2 * i);
-#pragma unroll
-        for (int u = 0; u < JB; ++u)
-          if (u < nj) {
-            double2 v = ld2_stream(Vb + (int64_t)u * ld + 2 * i);
-            acc[u] = fma(v.y, wv.y, fma(v.x, wv.x, acc[u]));
-          }
-      }
-    }
-    if ((n & 1) && gt == 0) {
-      const double wv = w[n - 1];
-#pragma unroll
-      for (int u = 0; u < JB; ++u)
-        if (u < nj) acc[u] = fma(Vb[(int64_t)u * ld + n - 1], wv, acc[u]);
+    switch (nj) {  // block-uniform; the remainder pass runs unmasked code too
+      case 8: dots_pass<8>(Vb, ld, n, w, acc); break;
+      case 7: dots_pass<7>(Vb, ld, n, w, acc); break;
+      case 6: dots_pass<6>(Vb, ld, n, w, acc); break;
+      case 5: dots_pass<5>(Vb, ld, n, w, acc); break;
+      case 4: dots_pass<4>(Vb, ld, n, w, acc); break;
+      case 3: dots_pass<3>(Vb, ld, n, w, acc); break;
+      case 2: dots_pass<2>(Vb, ld, n, w, acc); break;
+      default: dots_pass<1>(Vb, ld, n, w, acc); break;
     }
 #pragma unroll
     for (int u = 0; u < JB; ++u) {
@@ -321,7 +326,7 @@ int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, 
   GNK_REQUIRE(ctx && lay && d_V && d_w && d_h, "gnk_cgs_dots: null argument");
   GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_dots: k out of range");
   GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_dots: off/ld must be even");
-  int grid = stream_grid(ctx, lay->n_own / 2, 4);
+  int grid = stream_grid(ctx, lay->n_own / 2, 8);
   dots_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V + lay->off, lay->ld, lay->n_own, k, d_w + lay->off,
                                                       ctx->d_partials + PART_DOTS, ctx->d_tickets + TK_DOTS, d_h);
   GNK_LAUNCH_CHECK(ctx);
