@@ -241,6 +241,11 @@ def gauss_newton_krylow(
 
     JV = None
     jv_cap = 0
+    jv_valid = 0  # leading columns of JV that already hold J_current V (written by gnk_cgs_update_spmm)
+    # GNK_FUSED_UPDATE=1 lets the Gram-Schmidt update pass also write J_new V_k (saves the SpMM's re-read of V_k, 8nk
+    # bytes); measured at 4096^2: the fused kernel reaches 0.50 of the HBM roofline (2.55 ms at k = 30) against
+    # 0.95 / 1.00 for SpMM + update run separately (1.32 + 0.65 ms), 187 vs 200 it/s -> opt-in
+    fuse_update = is_bratu and os.environ.get("GNK_FUSED_UPDATE", "0") == "1"
     # GNK_FUSED_LS=1 forms J V_k inside the TSQR leaf (saves the n x k buffer and its 16nk bytes of traffic); measured
     # 14 % slower than SpMM + TSQR at 4096^2 because the leaf is issue-bound, so it is opt-in
     fuse_ls = is_bratu and os.environ.get("GNK_FUSED_LS", "0") == "1"
@@ -253,13 +258,20 @@ def gauss_newton_krylow(
         if not fused and k > jv_cap:
             jv_cap = min(MAX_COLUMNS, max(krylow.cap, k))
             JV = rt.empty(jv_cap * ldjv)
+            jv_valid = 0
         # projected operator and projected least squares  (:86-89)
         if fused:
             with rt.mark("spmm+tsqr", 8.0 * n_res_own * (k + 2)):
                 prob.d.tsqr_fused(jac_ev.expu, krylow.V, ld, k, F_cur, -1.0, blk)
+        elif jv_valid >= k:
+            pass  # every column of J V_k was already written by the fused Gram-Schmidt update pass
+        elif jv_valid == k - 1 and k > 1:
+            with rt.mark("spmm", 8.0 * n_res_own * 3):  # only the column appended since
+                jac_ev.matmat(krylow.col(k - 1), ld, 1, JV[(k - 1) * ldjv:], ldjv)
         else:
             with rt.mark("spmm", 8.0 * n_res_own * (2 * k + 1)):
                 jac_ev.matmat(krylow.V, ld, k, JV, ldjv)
+        jv_valid = 0
         if fused:
             pass
         elif ls_solver == "qr":
@@ -304,15 +316,22 @@ def gauss_newton_krylow(
         jac_ev = prob.jacobian(x_trial, aux=aux[1])  # e^x came out of the accepted trial
         njev += 1
 
+        # the update pass can also write J_new V_k for the next iteration (needs the JV buffer of this iteration)
+        k_before = krylow.k
+        sp = None
+        if (fuse_update and JV is not None and not fuse_ls and krylow.k < krylow.cap and krylow.k + 1 <= jv_cap
+                and not jac_ev.transposed and jac_ev.scale == 1.0):
+            sp = (jac_ev, JV, ldjv)
+        krylow.spmm_done = False
         try:
             if version == "res_old":
-                krylow.dev_update(jac_ev, F_cur, hx)
+                krylow.dev_update(jac_ev, F_cur, hx, sp)
             elif version == "res_new":
-                krylow.dev_update(jac_ev, F_trial, hx)
+                krylow.dev_update(jac_ev, F_trial, hx, sp)
             elif version == "jac_old_res_old":
-                krylow.dev_update(jac_ev_old, F_cur, hx)
+                krylow.dev_update(jac_ev_old, F_cur, hx, sp)
             elif version == "jac_old_res_new":
-                krylow.dev_update(jac_ev_old, F_trial, hx)
+                krylow.dev_update(jac_ev_old, F_trial, hx, sp)
             else:
                 raise ValueError(
                     "Variable version must be in ['res_old','res_new','jac_old_res_old','jac_old_res_new']"
@@ -327,6 +346,8 @@ def gauss_newton_krylow(
                 f"Warning: The genearlized krylow subspace is now identical to the whole parameter space at iteration = {iter}"
             )
 
+        if krylow.spmm_done:
+            jv_valid = k_before
         # the trial becomes the current point
         F_cur, F_trial = F_trial, F_cur
         prev_loss = float(vals[_SC_LOSS])
@@ -336,6 +357,7 @@ def gauss_newton_krylow(
 
         if iter % krylow_restart == 0:  # (:135-136)  x = V c equals the accepted trial point bit for bit
             set_c0(krylow.dev_start(x_trial))
+            jv_valid = 0
 
     if not success:
         print("Warning: The gauss_newton_krylow algorithm reached maximal iteration bound before terminating!")

@@ -51,6 +51,7 @@ class GeneralizedKrylowSubspace:
         self.reorth_passes = int(reorth_passes)
         self.k = 0
         self.V = None
+        self.spmm_done = False
         self._ready = False
 
     # ---------------------------------------------------------------------------------------------
@@ -102,9 +103,11 @@ class GeneralizedKrylowSubspace:
             _lib.check(rt.lib.gnk_combine(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(c), ptr(d), float(s),
                                           ptr(out), rt.stream), "gnk_combine")
 
-    def dev_update(self, jac_op, r, halo_exchange=None):
+    def dev_update(self, jac_op, r, halo_exchange=None, spmm=None):
         """Expand the basis with -J^T r orthogonalised against V_k (krylow.py:55-73).  Raises the same
-        exceptions as the reference; on Breakdown the basis is left unchanged."""
+        exceptions as the reference; on Breakdown the basis is left unchanged.  ``spmm=(stencil_jacobian, JV,
+        ldjv)`` lets the (last) Gram-Schmidt update pass also write J V_k for the current k columns
+        (gnk_cgs_update_spmm); returns True if it did."""
         if self.k == self.n_glob:
             raise GeneralizedKrylowSubspaceSpansEntireSpace
         rt, lib = self.rt, self.rt.lib
@@ -113,19 +116,30 @@ class GeneralizedKrylowSubspace:
         n = self.fields["n_own"]
         with rt.mark("spmv_t", 24.0 * n):
             jac_op.neg_rmatvec(r, self.w)
-        for _ in range(self.reorth_passes):
+        did_spmm = False
+        for ipass in range(self.reorth_passes):
             with rt.mark("cgs_dots", 8.0 * n * (self.k + 1)):
                 _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.w), ptr(self.h),
                                             rt.stream), "gnk_cgs_dots")
             rt.allreduce(self.h, self.k, 0)
-            with rt.mark("cgs_update", 8.0 * n * (self.k + 2)):
-                _lib.check(lib.gnk_cgs_update(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.h),
-                                              ptr(self.w), ptr(self.stats), rt.stream), "gnk_cgs_update")
+            if spmm is not None and ipass == self.reorth_passes - 1:
+                jn, JV, ldjv = spmm
+                d = jn.pb.dev
+                with rt.mark("cgs_update+spmm", 8.0 * n * (2 * self.k + 3)):
+                    _lib.check(lib.gnk_cgs_update_spmm(rt.ctx, C.byref(self.lay), C.byref(d.prm), ptr(jn.expu),
+                                                       ptr(self.V), self.k, ptr(self.h), ptr(self.w), ptr(self.stats),
+                                                       -1.0, ptr(JV), ldjv, rt.stream), "gnk_cgs_update_spmm")
+                did_spmm = True
+            else:
+                with rt.mark("cgs_update", 8.0 * n * (self.k + 2)):
+                    _lib.check(lib.gnk_cgs_update(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.h),
+                                                  ptr(self.w), ptr(self.stats), rt.stream), "gnk_cgs_update")
         rt.allreduce(self.stats, 2, 2)
         new = self.col(self.k)
         with rt.mark("normalize", 16.0 * n):
             _lib.check(lib.gnk_normalize(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8, ptr(new),
                                          ptr(self.flag), rt.stream), "gnk_normalize")
+        self.spmm_done = did_spmm
         if int(rt.read_i32(self.flag)[0]) != 0:
             raise GeneralizedKrylowSubspaceBreakdown(
                 "Normal residual is allready inside generalized Krylow Subspcae, there for gauss newton krylow "
@@ -133,6 +147,7 @@ class GeneralizedKrylowSubspace:
         if halo_exchange is not None:
             halo_exchange(self.V, 2, self.k * self.ld)
         self.k += 1
+        return did_spmm
 
     # ---- the reference's public interface (host ndarrays) -------------------------------------------
     @property

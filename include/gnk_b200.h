@@ -108,6 +108,15 @@ int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, 
 int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_h,
                    double* d_w, double* d_stats, void* stream);
 
+/* gnk_cgs_update fused with the NEXT outer iteration's gnk_stencil_apply: in the one pass over V_k that forms
+ * w -= V_k h it also writes JV[:, j] = sign * (M V[:, j]) for j < k with the Jacobian given by d_expu (the new one:
+ * gauss_newton_krylow.py:107 precedes the basis update :110-118), saving the re-read of V_k by the SpMM of
+ * gauss_newton_krylow.py:86.  Same arithmetic, bit for bit, as the two separate kernels.  JV columns hold the owned
+ * rows only (stride ldjv). */
+int gnk_cgs_update_spmm(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
+                        const double* d_V, int k, const double* d_h, double* d_w, double* d_stats, double sign,
+                        double* d_JV, int64_t ldjv, void* stream);
+
 /* ---- projected least squares (gauss_newton_krylow.py:16-36, :89) ------------------------------- */
 /* Householder TSQR of the n_rows x (k+1) panel [sign_a*A | y] (A column-major, stride lda) and
  * solution of min || sign_a*A d - y ||_2.  Results (device): d_out[0..k) = d, d_out[k] = ||R d||^2

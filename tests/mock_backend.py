@@ -179,6 +179,11 @@ class MockLib:
             s[1] = np.max(np.abs(wv)) if wv.size else 0.0
         return 0
 
+    def gnk_cgs_update_spmm(self, ctx, lay, prm, expu, V, k, h, w, stats, sign, JV, ldjv, stream):
+        lay_o = obj(lay)
+        self.gnk_stencil_apply(ctx, lay, prm, expu, V, lay_o.ld, k, sign, 0, JV, ldjv, 0, stream)
+        return self.gnk_cgs_update(ctx, lay, V, k, h, w, stats, stream)
+
     # ---- least squares: per-rank QR, gather of R factors, QR of the stack (the TSQR tree) ----
     def gnk_tsqr_ls(self, ctx, A, lda, n_rows, k, y, sign_a, out, stream):
         self.launches += 1

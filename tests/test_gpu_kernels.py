@@ -387,6 +387,46 @@ def test_fused_stencil_tsqr_matches_unfused(g, G, k):
     assert np.allclose(np.abs(vb[k + 4:]), np.abs(va[k + 4:]), rtol=1e-11)       # |diag R|
 
 
+@pytest.mark.parametrize("G,k", [(12, 1), (13, 5), (35, 8), (130, 7), (131, 20), (258, 30), (1030, 12)])
+def test_fused_update_spmm_matches_separate_kernels(g, G, k):
+    """gnk_cgs_update_spmm (Gram-Schmidt update that also writes J V_k) is bit-for-bit gnk_cgs_update + gnk_stencil_apply."""
+    _lib, device = _lib_mods()
+    pb = g.BratuPdeProblem(G, 5, 10)
+    d = pb.dev
+    rt = d.rt
+    lib = rt.lib
+    n, ld, off = d.fields["n_own"], d.ld, d.fields["off"]
+    rs = np.random.RandomState(G * 100 + k)
+    V = rt.zeros(k * ld)
+    for j in range(k):
+        d.upload_x(rs.normal(size=pb.n), V[j * ld:(j + 1) * ld])
+    u, E = d.new_col(), d.new_col()
+    d.upload_x(0.3 * rs.normal(size=pb.n), u)
+    d.residual_into(u, d.zero_col(), d.new_col(), E, d.scal_tmp, depth=0)
+    wh = rs.normal(size=pb.n)
+    w1, w2 = d.new_col(), d.new_col()
+    d.upload_x(wh, w1)
+    d.upload_x(wh, w2)
+    h = rt.zeros(128)
+    rt.upload(rs.normal(size=k), h[:k])
+    ldjv = (n + 15) // 16 * 16
+    JV1, JV2 = rt.zeros(k * ldjv), rt.zeros(k * ldjv)
+    s1, s2 = rt.zeros(2), rt.zeros(2)
+    d.apply(E, V, ld, k, -1.0, 0, JV1, ldjv, 0)
+    _lib.check(lib.gnk_cgs_update(rt.ctx, C.byref(d.lay), device.ptr(V), k, device.ptr(h), device.ptr(w1),
+                                  device.ptr(s1), rt.stream))
+    _lib.check(lib.gnk_cgs_update_spmm(rt.ctx, C.byref(d.lay), C.byref(d.prm), device.ptr(E), device.ptr(V), k,
+                                       device.ptr(h), device.ptr(w2), device.ptr(s2), -1.0, device.ptr(JV2), ldjv,
+                                       rt.stream))
+    a = rt.download(JV1).reshape(k, ldjv)[:, :n]
+    b = rt.download(JV2).reshape(k, ldjv)[:, :n]
+    assert np.array_equal(a, b)
+    wa, wb = rt.download(w1[off:off + n]), rt.download(w2[off:off + n])
+    assert rel(wb, wa) < 1e-14          # same products, accumulated over the columns in the same order
+    ra, rb = rt.read(s1, 2), rt.read(s2, 2)
+    assert abs(ra[0] - rb[0]) <= 1e-12 * ra[0] and abs(ra[1] - rb[1]) <= 1e-14 * ra[1]
+
+
 def test_tsqr_degenerate_inputs(g, capsys):
     """zero column -> scipy's solve_triangular error; all-zero right-hand side -> d = 0; single row; k at the limit."""
     rs = np.random.RandomState(11)

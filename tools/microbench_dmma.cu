@@ -55,6 +55,39 @@ __global__ void check(double* out) {
   out[threadIdx.x] = s;
   out[32 + threadIdx.x] = r;
 }
+// quad all-reduce: data in the A operand (lane l <-> A[l/4][l%4]), B all ones -> D[m][n] = sum of quad m, in every lane of the quad
+__global__ void check_quad(double* out) {
+  double v = 1.0 + threadIdx.x * 0.37;
+  double d0, d1;
+  dmma(d0, d1, v, 1.0, 0.0, 0.0);
+  double r = v;
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  out[threadIdx.x] = d0;
+  out[32 + threadIdx.x] = d1;
+  out[64 + threadIdx.x] = r;
+}
+// DFMA and DMMA interleaved: do they share one pipe?
+template <int NF, int NM>
+__global__ void thr_mix(double* out, long long* clk) {
+  double d0[4], d1[4], f[8];
+  double x = out[threadIdx.x];
+  for (int q = 0; q < 4; ++q) { d0[q] = q; d1[q] = -q; }
+  for (int q = 0; q < 8; ++q) f[q] = q + x;
+  long long t0 = clock64();
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int q = 0; q < NM; ++q) dmma(d0[q & 3], d1[q & 3], 1.0, x, d0[q & 3], d1[q & 3]);
+#pragma unroll
+    for (int q = 0; q < NF; ++q) f[q & 7] = fma(f[q & 7], 1.0000001, 1e-9);
+  }
+  long long t1 = clock64();
+  double s = 0;
+  for (int q = 0; q < 4; ++q) s += d0[q] + d1[q];
+  for (int q = 0; q < 8; ++q) s += f[q];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+}
 int main() {
   double* out; long long* clk; cudaMalloc(&out, 1 << 24); cudaMemset(out, 0, 1 << 24); cudaMalloc(&clk, 8 * 4096);
   long long h[4096]; double hv[64];
@@ -74,6 +107,25 @@ int main() {
   double mxd = 0; for (int i = 0; i < 32; ++i) { double d = hv[i] - hv[32 + i]; if (d < 0) d = -d; if (d > mxd) mxd = d; }
   printf("sum via DMMA %.17g  via shuffles %.17g  max |diff| %.3g  (all lanes equal: %d)\n", hv[0], hv[32], mxd,
          hv[0] == hv[31]);
+  check_quad<<<1, 32>>>(out); { double q[96]; cudaMemcpy(q, out, 96 * 8, cudaMemcpyDeviceToHost);
+    int ok = 1; for (int i = 0; i < 32; ++i) ok &= (q[i] == q[32 + i]) && (q[i] == q[4 * (i / 4)]);
+    double md = 0; for (int i = 0; i < 32; ++i) { double d = q[i] - q[64 + i]; if (d < 0) d = -d; if (d > md) md = d; }
+    printf("quad-sum via DMMA(A=data,B=ones): d0==d1 and uniform in quad: %d, max|diff| vs shuffles %.3g (q0 %.6f q7 %.6f)\n", ok, md, q[0], q[28]); }
+  {
+    auto runmix = [&](auto kern, const char* nm, int nf, int nm_) {
+      for (int warps = 8; warps <= 16; warps *= 2) {
+        kern<<<p.multiProcessorCount, warps * 32>>>(out, clk);
+        cudaMemcpy(h, clk, 8 * p.multiProcessorCount, cudaMemcpyDeviceToHost);
+        double mx = 0; for (int i = 0; i < p.multiProcessorCount; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("%s %2d warps/SM: %8.1f clk per iteration per SM-wide warp set -> %.2f clk/SMSP per (DFMA x%d + DMMA x%d)\n", nm, warps,
+               mx / N, mx / N / (warps / 4.0), nf, nm_);
+      }
+    };
+    runmix(thr_mix<16, 0>, "mix 16 DFMA + 0 DMMA", 16, 0);
+    runmix(thr_mix<0, 2>, "mix  0 DFMA + 2 DMMA", 0, 2);
+    runmix(thr_mix<16, 2>, "mix 16 DFMA + 2 DMMA", 16, 2);
+    runmix(thr_mix<16, 1>, "mix 16 DFMA + 1 DMMA", 16, 1);
+  }
   printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
