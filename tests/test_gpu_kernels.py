@@ -203,6 +203,22 @@ def test_tsqr_least_squares(g, n, k):
     assert rel(x, xr) < 1e-13 * max(cond, 10.0)
 
 
+@pytest.mark.parametrize("n,k", [(16384, 1), (16385, 2), (20001, 7), (33333, 8), (50001, 12), (65537, 15), (70001, 16),
+                                 (40003, 23), (100001, 24), (262147, 31)])
+def test_tsqr_warp_autonomous_leaf(g, n, k):
+    """large panels (>= 16384 rows, <= 32 columns) take the warp-autonomous leaf: odd row counts (8-byte tails of the
+    16-byte copies), every column-slot count, partial last tiles, warps without tiles."""
+    rs = np.random.RandomState(n + k)
+    A = rs.normal(size=(n, k)) @ (np.eye(k) + 0.3 * rs.normal(size=(k, k)))
+    y = rs.normal(size=n)
+    x = g.linear_least_squares(A, y)
+    xr = np.linalg.lstsq(A, y, rcond=None)[0]
+    assert rel(x, xr) < 1e-13 * max(np.linalg.cond(A), 10.0)
+    # scaling by a power of two changes no rounding: identical bits, and graded columns stay accurate
+    x2 = g.linear_least_squares(A * 2.0 ** 40, y * 2.0 ** 40)
+    assert np.array_equal(x, x2)
+
+
 def test_tsqr_scalar_block_and_rank_deficiency(g, capsys):
     _lib, device = _lib_mods()
     from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve
