@@ -130,16 +130,24 @@ __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_brat
 // out[:, col] = sign * Op * in[:, col];  grid = (k, j-tiles, row-tiles): the column index is the
 // fastest block coordinate so that the CTAs sharing one e^u tile are co-resident and the tile is
 // served from L2 after its first HBM read.
-template <bool VEC>
+// DOTS: the same pass also forms h[col] = in[:, col] . w over the owned rows (first half of krylow.py:64): the
+// Gram-Schmidt coefficients against V_k and the next outer iteration's J V_k both stream V_k once, and w (like e^u)
+// is shared by the k CTAs of a tile, so it costs one HBM read.  Per-CTA partial sums are reduced by the CTA that
+// arrives last, in a fixed order (deterministic).
+template <bool VEC, bool DOTS>
 __global__ void __launch_bounds__(TPBX) apply_kernel(gnk_layout lay, gnk_bratu prm, const double* __restrict__ expu,
                                                       const double* __restrict__ in, int64_t in_ld, double sign,
                                                       int transpose, int TR, double* __restrict__ out,
-                                                      int64_t out_ld, int64_t out_off) {
+                                                      int64_t out_ld, int64_t out_off, const double* __restrict__ w,
+                                                      double* __restrict__ partials, unsigned int* ticket,
+                                                      double* __restrict__ h) {
   constexpr int W = VEC ? 2 : 1;
   const int m = lay.m;
   const int col = blockIdx.x;
   const int j0 = W * (blockIdx.y * TPBX + threadIdx.x);
-  if (j0 >= m) return;
+  double acc = 0.0;
+  if (!DOTS && j0 >= m) return;
+  if (j0 < m) {
   const int rbeg = (int)blockIdx.z * TR;
   const int rend = min(rbeg + TR, lay.rows);
   const double* vb = in + (int64_t)col * in_ld + lay.off + j0;
@@ -169,8 +177,29 @@ __global__ void __launch_bounds__(TPBX) apply_kernel(gnk_layout lay, gnk_bratu p
     const double oa = apply_refbits(cu, cl, dga, cd, up.a, lf, mid.a, ra, dn.a);
     const double ob2 = VEC ? apply_refbits(cu, cl, dgb, cd, up.b, mid.a, mid.b, rt, dn.b) : 0.0;
     store_pair<VEC>(ob + ro, sign * oa, sign * ob2);
+    if (DOTS) {
+      Pair<VEC> wv = load_pair<VEC>(w + lay.off + j0 + ro);
+      acc = fma(mid.a, wv.a, acc);
+      if (VEC) acc = fma(mid.b, wv.b, acc);
+    }
     up = mid;
     mid = dn;
+  }
+  }
+  if (DOTS) {
+    __shared__ double sh[32];
+    acc = block_sum(acc, sh);
+    const unsigned int nb = gridDim.y * gridDim.z;
+    if (threadIdx.x == 0) partials[(size_t)col * nb + blockIdx.y * gridDim.z + blockIdx.z] = acc;
+    if (grid_arrive_last(ticket)) {
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      for (int j = wid; j < (int)gridDim.x; j += nw) {
+        double a = 0.0;
+        for (unsigned int b = lane; b < nb; b += 32) a += __ldcg(partials + (size_t)j * nb + b);
+        a = warp_sum(a);
+        if (lane == 0) h[j] = a;
+      }
+    }
   }
 }
 
@@ -392,11 +421,13 @@ int gnk_stencil_apply(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm,
   GNK_REQUIRE(grid.z <= 65535, "gnk_stencil_apply: too many row tiles");
   const double* e = (prm->lam == 0.0) ? nullptr : d_expu;
   if (vec)
-    apply_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr, d_out,
-                                                              out_ld, out_off);
+    apply_kernel<true, false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr,
+                                                                     d_out, out_ld, out_off, nullptr, nullptr, nullptr,
+                                                                     nullptr);
   else
-    apply_kernel<false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr, d_out,
-                                                               out_ld, out_off);
+    apply_kernel<false, false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr,
+                                                                      d_out, out_ld, out_off, nullptr, nullptr, nullptr,
+                                                                      nullptr);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -415,6 +446,40 @@ int gnk_stencil_normal_diag(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu
     normal_diag_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, tr, d_out);
   else
     normal_diag_kernel<false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, tr, d_out);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gnk_stencil_apply_dots(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
+                           const double* d_V, int64_t ldv, int k, double sign, double* d_JV, int64_t ldjv,
+                           const double* d_w, double* d_h, void* stream) {
+  GNK_REQUIRE(ctx && prm && d_V && d_JV && d_w && d_h, "gnk_stencil_apply_dots: null argument");
+  GNK_REQUIRE(check_layout(lay) == 0, "gnk_stencil_apply_dots: inconsistent stencil layout");
+  GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_stencil_apply_dots: k out of range");
+  GNK_REQUIRE(prm->lam == 0.0 || d_expu, "gnk_stencil_apply_dots: e^u diagonal required when lam != 0");
+  const bool vec = (lay->m % 2) == 0 && (ldv % 2) == 0 && (ldjv % 2) == 0 && (lay->ld % 2) == 0;
+  const int gx = (int)ceil_div(lay->m, (vec ? 2 : 1) * TPBX);
+  const int tr = pick_tr(ctx, gx, lay->rows, k);
+  dim3 grid(k, gx, (unsigned)ceil_div(lay->rows, tr));
+  GNK_REQUIRE(grid.z <= 65535, "gnk_stencil_apply_dots: too many row tiles");
+  const size_t need = sizeof(double) * (size_t)GNK_MAX_BASIS * grid.y * grid.z;
+  if (need > ctx->apart_bytes) {
+    GNK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (ctx->d_apart) GNK_CUDA(cudaFree(ctx->d_apart));
+    ctx->d_apart = nullptr;
+    ctx->apart_bytes = 0;
+    GNK_CUDA(cudaMalloc(&ctx->d_apart, need));
+    ctx->apart_bytes = need;
+  }
+  const double* e = (prm->lam == 0.0) ? nullptr : d_expu;
+  if (vec)
+    apply_kernel<true, true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_V, ldv, sign, 0, tr, d_JV, ldjv, 0,
+                                                                    d_w, ctx->d_apart, ctx->d_tickets + TK_APPLY_DOTS,
+                                                                    d_h);
+  else
+    apply_kernel<false, true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_V, ldv, sign, 0, tr, d_JV, ldjv,
+                                                                     0, d_w, ctx->d_apart,
+                                                                     ctx->d_tickets + TK_APPLY_DOTS, d_h);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -242,10 +242,18 @@ def gauss_newton_krylow(
     JV = None
     jv_cap = 0
     jv_valid = 0  # leading columns of JV that already hold J_current V (written by gnk_cgs_update_spmm)
-    # GNK_FUSED_UPDATE=1 lets the Gram-Schmidt update pass also write J_new V_k (saves the SpMM's re-read of V_k, 8nk
-    # bytes); measured at 4096^2: the fused kernel reaches 0.50 of the HBM roofline (2.55 ms at k = 30) against
-    # 0.95 / 1.00 for SpMM + update run separately (1.32 + 0.65 ms), 187 vs 200 it/s -> opt-in
-    fuse_update = is_bratu and os.environ.get("GNK_FUSED_UPDATE", "0") == "1"
+    # GNK_FUSED_DOTS=1: the Gram-Schmidt pass h = V_k^T w also writes J_new V_k for the next outer iteration
+    # (gnk_stencil_apply_dots; the next SpMM shrinks to the appended column).  GNK_FUSED_UPDATE=1 fuses the SpMM into
+    # the *update* pass instead.  Both are correct (J V bit-identical) but measured slower at 4096^2 than the separate
+    # kernels, which already run at 0.95-1.0 of the HBM roofline: k = 30: 2.07 ms (dots) / 2.55 ms (update) against
+    # 1.32 + 0.63 ms; the per-CTA reduction tail / the 8-row register tiles cost more than the saved pass over V_k.
+    # The fused h also differs from gnk_cgs_dots by summation order, which the degenerate linear runs amplify.
+    fuse_mode = None
+    if is_bratu and os.environ.get("GNK_FUSED_UPDATE", "0") == "1":
+        fuse_mode = "update"
+    elif is_bratu and os.environ.get("GNK_FUSED_DOTS", "0") == "1":
+        fuse_mode = "dots"
+    fuse_update = fuse_mode is not None
     # GNK_FUSED_LS=1 forms J V_k inside the TSQR leaf (saves the n x k buffer and its 16nk bytes of traffic); measured
     # 14 % slower than SpMM + TSQR at 4096^2 because the leaf is issue-bound, so it is opt-in
     fuse_ls = is_bratu and os.environ.get("GNK_FUSED_LS", "0") == "1"
@@ -321,7 +329,7 @@ def gauss_newton_krylow(
         sp = None
         if (fuse_update and JV is not None and not fuse_ls and krylow.k < krylow.cap and krylow.k + 1 <= jv_cap
                 and not jac_ev.transposed and jac_ev.scale == 1.0):
-            sp = (jac_ev, JV, ldjv)
+            sp = (jac_ev, JV, ldjv, fuse_mode)
         krylow.spmm_done = False
         try:
             if version == "res_old":

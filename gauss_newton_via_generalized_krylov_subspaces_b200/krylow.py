@@ -106,7 +106,8 @@ class GeneralizedKrylowSubspace:
     def dev_update(self, jac_op, r, halo_exchange=None, spmm=None):
         """Expand the basis with -J^T r orthogonalised against V_k (krylow.py:55-73).  Raises the same
         exceptions as the reference; on Breakdown the basis is left unchanged.  ``spmm=(stencil_jacobian, JV,
-        ldjv)`` lets the (last) Gram-Schmidt update pass also write J V_k for the current k columns
+        ldjv, mode)`` lets a Gram-Schmidt pass over V_k also write J V_k for the current k columns: mode "dots" fuses
+        it into the first dot-product pass (gnk_stencil_apply_dots), mode "update" into the last update pass
         (gnk_cgs_update_spmm); returns True if it did."""
         if self.k == self.n_glob:
             raise GeneralizedKrylowSubspaceSpansEntireSpace
@@ -117,13 +118,24 @@ class GeneralizedKrylowSubspace:
         with rt.mark("spmv_t", 24.0 * n):
             jac_op.neg_rmatvec(r, self.w)
         did_spmm = False
+        fuse_dots = spmm is not None and len(spmm) > 3 and spmm[3] == "dots"
         for ipass in range(self.reorth_passes):
-            with rt.mark("cgs_dots", 8.0 * n * (self.k + 1)):
-                _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.w), ptr(self.h),
-                                            rt.stream), "gnk_cgs_dots")
+            if fuse_dots and ipass == 0:
+                jn, JV, ldjv = spmm[:3]
+                d = jn.pb.dev
+                with rt.mark("spmm+cgs_dots", 8.0 * n * (2 * self.k + 3)):
+                    _lib.check(lib.gnk_stencil_apply_dots(rt.ctx, C.byref(self.lay), C.byref(d.prm), ptr(jn.expu),
+                                                          ptr(self.V), self.ld, self.k, -1.0, ptr(JV), ldjv,
+                                                          ptr(self.w), ptr(self.h), rt.stream),
+                               "gnk_stencil_apply_dots")
+                did_spmm = True
+            else:
+                with rt.mark("cgs_dots", 8.0 * n * (self.k + 1)):
+                    _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.w),
+                                                ptr(self.h), rt.stream), "gnk_cgs_dots")
             rt.allreduce(self.h, self.k, 0)
-            if spmm is not None and ipass == self.reorth_passes - 1:
-                jn, JV, ldjv = spmm
+            if spmm is not None and not fuse_dots and ipass == self.reorth_passes - 1:
+                jn, JV, ldjv = spmm[:3]
                 d = jn.pb.dev
                 with rt.mark("cgs_update+spmm", 8.0 * n * (2 * self.k + 3)):
                     _lib.check(lib.gnk_cgs_update_spmm(rt.ctx, C.byref(self.lay), C.byref(d.prm), ptr(jn.expu),

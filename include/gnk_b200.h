@@ -108,6 +108,15 @@ int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, 
 int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_h,
                    double* d_w, double* d_stats, void* stream);
 
+/* gnk_cgs_dots fused with the NEXT outer iteration's gnk_stencil_apply: one pass over V_k writes
+ * JV[:, j] = sign * (M V[:, j]) (Jacobian given by d_expu: the new one, gauss_newton_krylow.py:107 precedes the basis
+ * update :110-118) and h[j] = V[:, j] . w over the owned rows (krylow.py:64, first half), j < k.  Saves one of the six
+ * passes over V_k per outer iteration.  J V is bit-identical to gnk_stencil_apply; h differs from gnk_cgs_dots by
+ * summation order only.  d_w is a stored column, JV columns hold the owned rows (stride ldjv). */
+int gnk_stencil_apply_dots(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
+                           const double* d_V, int64_t ldv, int k, double sign, double* d_JV, int64_t ldjv,
+                           const double* d_w, double* d_h, void* stream);
+
 /* gnk_cgs_update fused with the NEXT outer iteration's gnk_stencil_apply: in the one pass over V_k that forms
  * w -= V_k h it also writes JV[:, j] = sign * (M V[:, j]) for j < k with the Jacobian given by d_expu (the new one:
  * gauss_newton_krylow.py:107 precedes the basis update :110-118), saving the re-read of V_k by the SpMM of

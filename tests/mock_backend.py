@@ -179,6 +179,10 @@ class MockLib:
             s[1] = np.max(np.abs(wv)) if wv.size else 0.0
         return 0
 
+    def gnk_stencil_apply_dots(self, ctx, lay, prm, expu, V, ldv, k, sign, JV, ldjv, w, h, stream):
+        self.gnk_stencil_apply(ctx, lay, prm, expu, V, ldv, k, sign, 0, JV, ldjv, 0, stream)
+        return self.gnk_cgs_dots(ctx, lay, V, k, w, h, stream)
+
     def gnk_cgs_update_spmm(self, ctx, lay, prm, expu, V, k, h, w, stats, sign, JV, ldjv, stream):
         lay_o = obj(lay)
         self.gnk_stencil_apply(ctx, lay, prm, expu, V, lay_o.ld, k, sign, 0, JV, ldjv, 0, stream)

@@ -443,6 +443,45 @@ def test_fused_update_spmm_matches_separate_kernels(g, G, k):
     assert abs(ra[0] - rb[0]) <= 1e-12 * ra[0] and abs(ra[1] - rb[1]) <= 1e-14 * ra[1]
 
 
+@pytest.mark.parametrize("G,k", [(12, 1), (13, 5), (35, 8), (130, 7), (131, 20), (258, 30), (1030, 12)])
+def test_fused_spmm_dots_matches_separate_kernels(g, G, k):
+    """gnk_stencil_apply_dots: J V_k bit-for-bit gnk_stencil_apply, h = V_k^T w equal to gnk_cgs_dots up to summation order."""
+    _lib, device = _lib_mods()
+    pb = g.BratuPdeProblem(G, 5, 10)
+    d = pb.dev
+    rt = d.rt
+    lib = rt.lib
+    n, ld, off = d.fields["n_own"], d.ld, d.fields["off"]
+    rs = np.random.RandomState(G * 100 + k)
+    Vh = rs.normal(size=(k, pb.n))
+    V = rt.zeros(k * ld)
+    for j in range(k):
+        d.upload_x(Vh[j], V[j * ld:(j + 1) * ld])
+    u, E, w = d.new_col(), d.new_col(), d.new_col()
+    d.upload_x(0.3 * rs.normal(size=pb.n), u)
+    d.residual_into(u, d.zero_col(), d.new_col(), E, d.scal_tmp, depth=0)
+    wh = rs.normal(size=pb.n)
+    d.upload_x(wh, w)
+    ldjv = (n + 15) // 16 * 16
+    JV1, JV2 = rt.zeros(k * ldjv), rt.zeros(k * ldjv)
+    h1, h2 = rt.zeros(128), rt.zeros(128)
+    d.apply(E, V, ld, k, -1.0, 0, JV1, ldjv, 0)
+    _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(d.lay), device.ptr(V), k, device.ptr(w), device.ptr(h1), rt.stream))
+    outs = []
+    for _ in range(2):  # twice: the self-resetting ticket and the run-to-run determinism of the reduction
+        _lib.check(lib.gnk_stencil_apply_dots(rt.ctx, C.byref(d.lay), C.byref(d.prm), device.ptr(E), device.ptr(V), ld,
+                                              k, -1.0, device.ptr(JV2), ldjv, device.ptr(w), device.ptr(h2),
+                                              rt.stream))
+        outs.append(rt.read(h2, k))
+    assert np.array_equal(outs[0], outs[1])
+    a = rt.download(JV1).reshape(k, ldjv)[:, :n]
+    b = rt.download(JV2).reshape(k, ldjv)[:, :n]
+    assert np.array_equal(a, b)
+    href = Vh @ wh
+    scale = np.linalg.norm(Vh, axis=1) * np.linalg.norm(wh)
+    assert np.all(np.abs(outs[0] - href) <= 1e-14 * scale) and np.all(np.abs(rt.read(h1, k) - href) <= 1e-14 * scale)
+
+
 def test_tsqr_degenerate_inputs(g, capsys):
     """zero column -> scipy's solve_triangular error; all-zero right-hand side -> d = 0; single row; k at the limit."""
     rs = np.random.RandomState(11)
