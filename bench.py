@@ -288,7 +288,10 @@ if __name__ == "__main__":
     args = parse()
     # the contract is ONE JSON line on stdout: the solvers' own prints (the reference's "reached maximal iteration
     # bound" warning etc.) go to stderr
-    real_stdout = sys.stdout
+    # -- at the file-descriptor level, so that prints from C libraries (e.g. NCCL's version banner) go there too
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     with contextlib.redirect_stdout(sys.stderr):
         _emit = print
 

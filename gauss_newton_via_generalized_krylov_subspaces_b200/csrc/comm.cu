@@ -99,15 +99,164 @@ int ensure_gather(gnk_ctx* ctx, size_t bytes, cudaStream_t st) {
   return 0;
 }
 
+
+// =================================================================================================
+// Peer-memory path (one node, NVLink/NVSwitch): every rank owns a "mailbox" in its HBM that all peers map with
+// CUDA IPC.  A collective is ONE single-CTA kernel: write my contribution into every peer's mailbox with plain
+// stores (they travel over NVLink), fence, raise my flag in every peer's mailbox (st.release.sys), wait until all
+// peers' flags in MY mailbox carry this collective's sequence number (ld.acquire.sys), then reduce the slots in rank
+// order out of local memory.  The messages are <= 85 KB (k doubles, 2 scalars, a (k+1)^2 triangle, two grid rows), so
+// the cost is NVLink latency (~2-3 us) instead of NCCL's ~20 us launch+protocol path, and one launch instead of two.
+// Slots are double-buffered on the parity of the sequence number: a rank can be at most one collective ahead of a
+// peer (it cannot finish collective s without the peer's flag s), so slot parity s is never overwritten before the
+// peer has left collective s-2.  Results are bitwise identical on all ranks (same rank-ordered reduction).
+// Mailbox layout (bytes): [0, 4096) flags: u64 gather[16], u64 halo[2] at +1024;
+//                         gather data 2 x nranks x P2P_GMAX doubles; halo data 2 parities x 2 sides x P2P_HMAX doubles.
+// =================================================================================================
+constexpr int P2P_MAXR = 16;
+constexpr int64_t P2P_GMAX = (int64_t)GNK_MAX_BASIS * GNK_MAX_BASIS;  // largest gather: one R triangle
+constexpr int64_t P2P_HMAX = 2 * 16384;                              // largest halo message: 2 grid rows of 16384
+constexpr size_t P2P_FLAG_BYTES = 4096;
+constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+__host__ __device__ inline size_t p2p_gather_off(int nranks, int parity, int r) {
+  return P2P_FLAG_BYTES + sizeof(double) * (size_t)((parity * nranks + r) * P2P_GMAX);
+}
+__host__ __device__ inline size_t p2p_halo_off(int nranks, int parity, int side) {
+  return P2P_FLAG_BYTES + sizeof(double) * (size_t)(2 * nranks * P2P_GMAX) +
+         sizeof(double) * (size_t)((parity * 2 + side) * P2P_HMAX);
+}
+inline size_t p2p_bytes(int nranks) { return p2p_halo_off(nranks, 2, 0); }
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= seq; a peer that never arrives (diverged control flow, dead process) must not hang the GPU
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long seq) {
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < seq) {
+    if (global_ns() - t0 > P2P_TIMEOUT_NS) __trap();
+  }
+}
+__device__ __forceinline__ double ld_volatile(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// op: 0 sum, 1 max, 2 (sum, max) pair as in gnk_comm_allreduce, 3 no reduction: out receives the nranks x count stack
+__global__ void __launch_bounds__(1024) p2p_gather_kernel(void* const* __restrict__ peers, int rank, int nranks,
+                                                           const double* __restrict__ src, int count, int op,
+                                                           unsigned long long seq, double* __restrict__ out) {
+  const int parity = (int)(seq & 1ull);
+  for (int r = 0; r < nranks; ++r) {
+    double* dst = reinterpret_cast<double*>(static_cast<char*>(peers[r]) + p2p_gather_off(nranks, parity, rank));
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  char* mine = static_cast<char*>(peers[rank]);
+  if ((int)threadIdx.x < nranks) {
+    unsigned long long* theirs = reinterpret_cast<unsigned long long*>(peers[threadIdx.x]);
+    st_release_sys(theirs + rank, seq);
+    wait_flag(reinterpret_cast<const unsigned long long*>(mine) + threadIdx.x, seq);
+  }
+  __syncthreads();
+  if (op == 3) {
+    for (int r = 0; r < nranks; ++r) {
+      const double* g = reinterpret_cast<const double*>(mine + p2p_gather_off(nranks, parity, r));
+      for (int i = threadIdx.x; i < count; i += blockDim.x) out[(int64_t)r * count + i] = ld_volatile(g + i);
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    double a = ld_volatile(reinterpret_cast<const double*>(mine + p2p_gather_off(nranks, parity, 0)) + i);
+    const bool is_max = (op == 1) || (op == 2 && i == 1);
+    for (int r = 1; r < nranks; ++r) {
+      const double b = ld_volatile(reinterpret_cast<const double*>(mine + p2p_gather_off(nranks, parity, r)) + i);
+      a = is_max ? fmax(a, b) : a + b;
+    }
+    out[i] = a;
+  }
+}
+
+// own0: first owned double of the stored column; cnt = depth * m doubles per message
+__global__ void __launch_bounds__(1024) p2p_halo_kernel(void* const* __restrict__ peers, int rank, int nranks,
+                                                         double* __restrict__ own0, int64_t cnt, int64_t rows_m,
+                                                         int has_lo, int has_hi, unsigned long long seq) {
+  const int parity = (int)(seq & 1ull);
+  // my first rows become the lower neighbour's upper halo (its side 1), my last rows the upper neighbour's side 0
+  if (has_lo) {
+    double* dst = reinterpret_cast<double*>(static_cast<char*>(peers[rank - 1]) + p2p_halo_off(nranks, parity, 1));
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = own0[i];
+  }
+  if (has_hi) {
+    double* dst = reinterpret_cast<double*>(static_cast<char*>(peers[rank + 1]) + p2p_halo_off(nranks, parity, 0));
+    const double* srcp = own0 + rows_m - cnt;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = srcp[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  char* mine = static_cast<char*>(peers[rank]);
+  const unsigned long long* myflags = reinterpret_cast<const unsigned long long*>(mine + 1024);
+  if (threadIdx.x == 0 && has_lo) {
+    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(peers[rank - 1]) + 1024) + 1, seq);
+    wait_flag(myflags + 0, seq);
+  }
+  if (threadIdx.x == 32 && has_hi) {
+    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(peers[rank + 1]) + 1024) + 0, seq);
+    wait_flag(myflags + 1, seq);
+  }
+  __syncthreads();
+  if (has_lo) {
+    const double* g = reinterpret_cast<const double*>(mine + p2p_halo_off(nranks, parity, 0));
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) own0[i - cnt] = ld_volatile(g + i);
+  }
+  if (has_hi) {
+    const double* g = reinterpret_cast<const double*>(mine + p2p_halo_off(nranks, parity, 1));
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) own0[rows_m + i] = ld_volatile(g + i);
+  }
+}
+
+int p2p_gather(gnk_ctx* ctx, const double* d_src, int64_t count, int op, double* d_out, cudaStream_t st) {
+  ctx->p2p_seq++;
+  const int threads = count >= 1024 ? 1024 : (count > 256 ? 512 : 256);
+  p2p_gather_kernel<<<1, threads, 0, st>>>(ctx->d_p2p_peer, ctx->rank, ctx->nranks, d_src, (int)count, op, ctx->p2p_seq,
+                                           d_out);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 }  // namespace
 
 int gnk_comm_allgather_doubles(gnk_ctx* ctx, const double* d_send, double* d_recv, int64_t count, void* stream) {
+  if (ctx->p2p_ready && count <= P2P_GMAX) return p2p_gather(ctx, d_send, count, 3, d_recv, (cudaStream_t)stream);
   GNK_REQUIRE(ctx->nccl_comm, "all-gather without a communicator");
   GNK_NCCL(g_nccl.AllGather(d_send, d_recv, (size_t)count, NCCL_F64, (NcclComm)ctx->nccl_comm, (cudaStream_t)stream));
   return 0;
 }
 
 void gnk_comm_teardown(gnk_ctx* ctx) {
+  if (ctx->p2p_local) {
+    cudaDeviceSynchronize();
+    for (int r = 0; r < ctx->nranks && r < P2P_MAXR; ++r)
+      if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    if (ctx->d_p2p_peer) cudaFree(ctx->d_p2p_peer);
+    cudaFree(ctx->p2p_local);
+    ctx->p2p_local = nullptr;
+    ctx->d_p2p_peer = nullptr;
+    ctx->p2p_ready = 0;
+  }
   if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((NcclComm)ctx->nccl_comm);
   ctx->nccl_comm = nullptr;
 }
@@ -139,6 +288,48 @@ int gnk_comm_init(gnk_ctx* ctx, const void* id128, int rank, int nranks) {
   return 0;
 }
 
+int gnk_comm_p2p_export(gnk_ctx* ctx, void* out_handle64) {
+  GNK_REQUIRE(ctx && out_handle64, "gnk_comm_p2p_export: null argument");
+  GNK_REQUIRE(ctx->nranks >= 2 && ctx->nranks <= P2P_MAXR, "gnk_comm_p2p_export: needs 2..16 ranks (call gnk_comm_init first)");
+  GNK_REQUIRE(!ctx->p2p_local, "gnk_comm_p2p_export: mailbox already exported");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  GNK_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = p2p_bytes(ctx->nranks);
+  GNK_CUDA(cudaMalloc(&ctx->p2p_local, bytes));
+  GNK_CUDA(cudaMemset(ctx->p2p_local, 0, bytes));
+  GNK_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  GNK_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_local));
+  memcpy(out_handle64, &h, sizeof(h));
+  return 0;
+}
+
+int gnk_comm_p2p_attach(gnk_ctx* ctx, const void* handles) {
+  GNK_REQUIRE(ctx && handles && ctx->p2p_local, "gnk_comm_p2p_attach: export the local mailbox first");
+  GNK_CUDA(cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->nranks; ++r) {
+    if (r == ctx->rank) {
+      ctx->p2p_peer[r] = ctx->p2p_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + 64 * (size_t)r, sizeof(h));
+    GNK_CUDA(cudaIpcOpenMemHandle(&ctx->p2p_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  GNK_CUDA(cudaMalloc(&ctx->d_p2p_peer, sizeof(void*) * P2P_MAXR));
+  GNK_CUDA(cudaMemcpy(ctx->d_p2p_peer, ctx->p2p_peer, sizeof(void*) * P2P_MAXR, cudaMemcpyHostToDevice));
+  ctx->p2p_seq = 0;
+  ctx->p2p_hseq = 0;
+  ctx->p2p_ready = 1;
+  return 0;
+}
+
+int gnk_comm_p2p_enabled(gnk_ctx* ctx) { return ctx ? ctx->p2p_ready : 0; }
+int gnk_comm_p2p_disable(gnk_ctx* ctx) {
+  if (ctx) ctx->p2p_ready = 0;
+  return 0;
+}
+
 int gnk_comm_size(gnk_ctx* ctx) { return ctx ? ctx->nranks : 0; }
 
 int gnk_comm_allreduce(gnk_ctx* ctx, double* d_buf, int count, int op, void* stream) {
@@ -146,6 +337,7 @@ int gnk_comm_allreduce(gnk_ctx* ctx, double* d_buf, int count, int op, void* str
   GNK_REQUIRE(count >= 1 && count <= 256 && op >= 0 && op <= 2, "gnk_comm_allreduce: bad count/op");
   if (ctx->nranks == 1) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->p2p_ready) return p2p_gather(ctx, d_buf, count, op, d_buf, st);
   if (int rc = ensure_gather(ctx, sizeof(double) * 256 * (size_t)ctx->nranks, st)) return rc;
   if (int rc = gnk_comm_allgather_doubles(ctx, d_buf, ctx->d_gather, count, stream)) return rc;
   rank_reduce_kernel<<<(count + 127) / 128, 128, 0, st>>>(ctx->d_gather, ctx->nranks, count, op, d_buf);
@@ -157,11 +349,18 @@ int gnk_comm_halo_exchange(gnk_ctx* ctx, const gnk_layout* lay, double* d_col, i
   GNK_REQUIRE(ctx && lay && d_col, "gnk_comm_halo_exchange: null argument");
   GNK_REQUIRE(depth >= 1 && depth <= lay->halo && depth <= lay->rows, "gnk_comm_halo_exchange: bad depth");
   if (ctx->nranks == 1) return 0;
-  GNK_REQUIRE(ctx->nccl_comm, "gnk_comm_halo_exchange: no communicator");
   cudaStream_t st = (cudaStream_t)stream;
-  NcclComm comm = (NcclComm)ctx->nccl_comm;
   const size_t cnt = (size_t)depth * lay->m;
   double* own0 = d_col + lay->off;
+  if (ctx->p2p_ready && (int64_t)cnt <= P2P_HMAX) {
+    ctx->p2p_hseq++;
+    p2p_halo_kernel<<<1, 1024, 0, st>>>(ctx->d_p2p_peer, ctx->rank, ctx->nranks, own0, (int64_t)cnt,
+                                        (int64_t)lay->rows * lay->m, lay->has_lo, lay->has_hi, ctx->p2p_hseq);
+    GNK_LAUNCH_CHECK(ctx);
+    return 0;
+  }
+  GNK_REQUIRE(ctx->nccl_comm, "gnk_comm_halo_exchange: no communicator");
+  NcclComm comm = (NcclComm)ctx->nccl_comm;
   GNK_NCCL(g_nccl.GroupStart());
   if (lay->has_lo) {
     GNK_NCCL(g_nccl.Send(own0, cnt, NCCL_F64, ctx->rank - 1, comm, st));

@@ -27,6 +27,14 @@ struct gnk_ctx {
   size_t gather_bytes = 0;
   // pinned host scalars for the C-side loops (cgls)
   double* h_pinned = nullptr;
+  // peer-memory mailboxes (comm.cu): one device block per rank, mapped into every peer of the node with CUDA IPC;
+  // the small all-gathers and the halo rows are written straight into the peers' mailboxes over NVLink
+  void* p2p_local = nullptr;          // this rank's mailbox
+  void* p2p_peer[16] = {nullptr};     // every rank's mailbox as seen from this process (own entry = p2p_local)
+  void** d_p2p_peer = nullptr;        // the same table in device memory
+  unsigned long long p2p_seq = 0;     // gathers issued so far (identical on all ranks: same call sequence)
+  unsigned long long p2p_hseq = 0;    // halo exchanges issued so far
+  int p2p_ready = 0;
   // per-CTA partial dot products of gnk_stencil_apply_dots (k * CTAs-per-column doubles, grown on demand)
   double* d_apart = nullptr;
   size_t apart_bytes = 0;

@@ -50,6 +50,27 @@ class Runtime:
         dist.broadcast_object_list(box, src=0)
         idbuf = (C.c_char * 128).from_buffer_copy(box[0])
         _lib.check(self.lib.gnk_comm_init(self.ctx, idbuf, self.rank, self.world), "gnk_comm_init")
+        self._attach_peer_mailboxes(dist)
+
+    def _attach_peer_mailboxes(self, dist):
+        """One-node runs: map every rank's mailbox with CUDA IPC so that the small all-gathers and the halo rows go
+        over NVLink as plain stores from single kernels (comm.cu).  Any failure leaves the NCCL path in use; all
+        ranks take the same decision.  GNK_P2P=0 disables it."""
+        lib = self.lib
+        if os.environ.get("GNK_P2P", "1") == "0" or not hasattr(lib, "gnk_comm_p2p_export") or self.world > 16:
+            return
+        h = (C.c_char * 64)()
+        rc = lib.gnk_comm_p2p_export(self.ctx, h)
+        box = [None] * self.world
+        dist.all_gather_object(box, (int(rc), bytes(h)))
+        if any(r != 0 for r, _ in box):
+            return
+        allh = (C.c_char * (64 * self.world)).from_buffer_copy(b"".join(b for _, b in box))
+        rc = lib.gnk_comm_p2p_attach(self.ctx, allh)
+        ok = [None] * self.world
+        dist.all_gather_object(ok, int(rc))
+        if any(r != 0 for r in ok):  # e.g. no peer access between some pair of devices: everybody stays on NCCL
+            lib.gnk_comm_p2p_disable(self.ctx)
 
     # -- helpers -----------------------------------------------------------------------------------
     @property

@@ -192,6 +192,16 @@ int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, double rtol, 
 int gnk_comm_unique_id(void* out128);
 int gnk_comm_init(gnk_ctx* ctx, const void* id128, int rank, int nranks);
 int gnk_comm_size(gnk_ctx* ctx);
+/* Peer-memory collectives for the ranks of one NVLink/NVSwitch node (optional, after gnk_comm_init): every rank
+ * exports a mailbox in its HBM as a 64-byte CUDA IPC handle, the host gathers the nranks handles (rank order, any
+ * out-of-band channel) and attaches them.  From then on gnk_comm_allreduce, the TSQR triangle gather and
+ * gnk_comm_halo_exchange are single kernels that store into the peers' mailboxes over NVLink and spin on flags there
+ * instead of NCCL calls (same fixed rank-ordered reductions, bitwise identical results).  If either call fails the
+ * NCCL path stays in use. */
+int gnk_comm_p2p_export(gnk_ctx* ctx, void* out_handle64);
+int gnk_comm_p2p_attach(gnk_ctx* ctx, const void* handles /* nranks x 64 bytes */);
+int gnk_comm_p2p_enabled(gnk_ctx* ctx);
+int gnk_comm_p2p_disable(gnk_ctx* ctx); /* back to the NCCL path (all ranks must call it together) */
 /* in-place fixed-order sum (op 0) / max (op 1) of `count` <= 256 doubles over all ranks:
  * all-gather followed by the same rank-ordered reduction everywhere (bitwise identical results). */
 int gnk_comm_allreduce(gnk_ctx* ctx, double* d_buf, int count, int op, void* stream);
