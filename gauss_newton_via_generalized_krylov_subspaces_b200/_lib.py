@@ -66,6 +66,8 @@ SIGNATURES = {
     "gnk_axpby": (_I, [_P, _L, _D, _P, _D, _P, _P, _P]),
     "gnk_dot": (_I, [_P, _L, _P, _P, _P, _P]),
     "gnk_cgls": (_I, [_P, C.POINTER(LinOp), _P, _D, _I, _P, _P, C.POINTER(_L), _P]),
+    "gnk_rosenbrock_residual": (_I, [_P, _L, _D, _P, _P, _P]),
+    "gnk_rosenbrock_jacobian": (_I, [_P, _L, _D, _P, _P, _P, _P]),
     "gnk_comm_unique_id": (_I, [_P]),
     "gnk_comm_init": (_I, [_P, _P, _I, _I]),
     "gnk_comm_size": (_I, [_P]),

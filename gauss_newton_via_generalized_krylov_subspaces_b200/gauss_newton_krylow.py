@@ -29,6 +29,7 @@ from .krylow import (GeneralizedKrylowSubspace, GeneralizedKrylowSubspaceBreakdo
                      GeneralizedKrylowSubspaceSpansEntireSpace, MAX_COLUMNS)
 from .partition import flat_layout_fields, round_up
 from .regression_result import RegressionResult
+from .rosenbrock_problem import RosenbrockDeviceProblem
 
 _NB = _lib.GNK_MAX_BASIS
 # layout of the per-iteration scalar block (device, one D2H read per Armijo trial)
@@ -37,9 +38,12 @@ _SC_CPREV = _SC_LOSS + 2  # sum(c_prev^2)
 _BLK = _SC_CPREV + 6
 
 
-def resolve_problem(res, jac, x0, args):
+def resolve_problem(res, jac, x0, args, native_rosenbrock=False):
     if BratuDeviceProblem.match(res, jac) and not args:
         return BratuDeviceProblem(res, jac)
+    if native_rosenbrock and RosenbrockDeviceProblem.match(res, jac, args) \
+            and os.environ.get("GNK_NATIVE_ROSENBROCK", "1") != "0":
+        return RosenbrockDeviceProblem(x0)
     return HostCallableProblem(res, jac, x0, args)
 
 
@@ -187,7 +191,7 @@ def gauss_newton_krylow(
     success = False
     x0_resident = isinstance(x0, DeviceVector) and x0._t is not None  # a start vector already in HBM
     x0_host = None if x0_resident else np.asarray(x0, dtype=np.float64).reshape(-1)
-    prob = resolve_problem(res, jac, x0 if x0_resident else x0_host, args)
+    prob = resolve_problem(res, jac, x0 if x0_resident else x0_host, args, native_rosenbrock=True)
     if krylow_restart is None:
         krylow_restart = max_iter
 
@@ -216,7 +220,8 @@ def gauss_newton_krylow(
     x_trial = prob.new_sol()
     krylow.dev_combine(c, None, 0.0, x_trial)
     is_bratu = isinstance(prob, BratuDeviceProblem)
-    if not is_bratu:  # residual-space size of a foreign callable is known after its first evaluation
+    native = is_bratu or getattr(prob, "device_native", False)  # res / jac have device twins: no host evaluation
+    if not native:  # residual-space size of a foreign callable is known after its first evaluation
         r0 = np.asarray(res(prob.download_global(x_trial), *args), dtype=np.float64).reshape(-1)
         prob._ensure_res_layout(r0.shape[0])
     F_cur, F_trial = prob.new_res(), prob.new_res()
@@ -227,7 +232,7 @@ def gauss_newton_krylow(
     aux = [prob.new_sol() for _ in range(3)] if use_aux else [None, None, None]  # e^x: J_cur, trial, spare
     hx = prob.d.halo_exchange if (is_bratu and prob.distributed) else None
 
-    if is_bratu:
+    if native:
         prob.residual(x_trial, F_cur, loss_slot, aux=None)
     else:
         rt.upload(r0, F_cur[:n_res_own])

@@ -185,6 +185,15 @@ typedef struct {
 int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, double rtol, int preconditioner,
              double* d_x, double* d_work, int64_t* iters, void* stream);
 
+/* ---- chained Rosenbrock problem on the device (rosenbrock_problem.py:8-19) -------------- */
+/* F = sqrt2 * [10 (x[1:] - x[:-1]^2) ; 1 - x[:-1]]  (2p-2 values), numpy's rounding order (res, :8-12). */
+int gnk_rosenbrock_residual(gnk_ctx* ctx, int64_t p, double sqrt2, const double* d_x, double* d_F, void* stream);
+/* values of J(x) (jac, :14-19) in CSR form, 3(p-1) doubles: row i < p-1: (i, -20 sqrt2 x_i), (i+1, 10 sqrt2); row
+ * p-1+i: (i, -sqrt2) -- and of J^T in CSR form (row pointer 0, 2, 5, ..., 3j-1, ..., 3(p-1)); the index arrays are
+ * fixed and supplied by the host to gnk_spmm_csr. */
+int gnk_rosenbrock_jacobian(gnk_ctx* ctx, int64_t p, double sqrt2, const double* d_x, double* d_val,
+                            double* d_val_t, void* stream);
+
 /* ---- multi-GPU plumbing (row slabs) -------------------------------------------------- */
 /* NCCL is owned by the library: rank 0 calls gnk_comm_unique_id, the 128 bytes travel by any
  * out-of-band channel (the Python host broadcasts them with torch.distributed), every rank calls

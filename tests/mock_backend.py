@@ -239,6 +239,31 @@ class MockLib:
                 A @ vin[j * in_ld + in_off: j * in_ld + in_off + ncol])
         return 0
 
+    # ---- chained Rosenbrock (rosenbrock_problem.py:8-19) ----
+    def gnk_rosenbrock_residual(self, ctx, p, sqrt2, x, F, stream):
+        self.launches += 1
+        xv = arr(x, p)
+        head = xv[:-1]
+        arr(F, 2 * p - 2)[:] = sqrt2 * np.concatenate([10 * (xv[1:] - head ** 2), 1 - head])
+        return 0
+
+    def gnk_rosenbrock_jacobian(self, ctx, p, sqrt2, x, val, val_t, stream):
+        import scipy.sparse as sp
+        self.launches += 1
+        xv = arr(x, p)
+        q = p - 1
+        i = np.arange(q)
+        rows = np.concatenate([i, i, q + i])
+        cols = np.concatenate([i, i + 1, i])
+        vals = sqrt2 * np.concatenate([-20.0 * xv[:-1], np.full(q, 10.0), np.full(q, -1.0)])
+        A = sp.csr_array(sp.coo_array((vals, (rows, cols)), shape=(2 * q, p)))
+        A.sort_indices()
+        AT = sp.csr_array(A.T)
+        AT.sort_indices()
+        arr(val, 3 * q)[:] = A.data
+        arr(val_t, 3 * q)[:] = AT.data
+        return 0
+
     def gnk_csr_row_sumsq(self, ctx, n_rows, rowptr, val, out, stream):
         self.launches += 1
         rp = arr(rowptr, n_rows + 1, np.int32)

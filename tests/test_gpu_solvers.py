@@ -237,6 +237,42 @@ def test_rosenbrock(g, tag, capsys):
     assert rp.error(out.x) < 1e-10
 
 
+def test_rosenbrock_device_native_callbacks(g, monkeypatch):
+    """res / jac of rosenbrock_problem have device twins (csrc/rosenbrock.cu).  The kernels reproduce the
+    host functions bit for bit, gauss_newton_krylow picks them up for exactly these two callables, and the whole
+    trajectory is bitwise the one of the host-callable path."""
+    import ctypes as C
+    import scipy.sparse as sp
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import _lib, rosenbrock_problem as rp
+    from gauss_newton_via_generalized_krylov_subspaces_b200.device import ptr
+    from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import resolve_problem
+    rt = g.get_runtime()
+    x0 = Golden("rosenbrock")["x0_i"]
+    prob = resolve_problem(rp.res, rp.jac, x0, (), native_rosenbrock=True)
+    assert isinstance(prob, rp.RosenbrockDeviceProblem)
+    assert not isinstance(resolve_problem(lambda x: rp.res(x), rp.jac, x0, (), native_rosenbrock=True),
+                          rp.RosenbrockDeviceProblem)       # any other callable is user code: host path
+    x, F, slot = prob.new_sol(), prob.new_res(), rt.zeros(2)
+    prob.upload_x(x0, x)
+    prob.residual(x, F, slot)
+    rh = rp.res(x0)
+    assert np.array_equal(rt.download(F[:prob.n_res]), rh)
+    assert abs(rt.read(slot, 1)[0] - np.sum(rh * rh)) <= 1e-13 * np.sum(rh * rh)
+    J = prob.jacobian(x)
+    A = sp.csr_array(rp.jac(x0))
+    A.sort_indices()
+    AT = sp.csr_array(A.T)
+    AT.sort_indices()
+    assert np.array_equal(rt.download(J.val), A.data) and np.array_equal(rt.download(J.val_t), AT.data)
+    assert np.array_equal(rt.download(prob.rowptr), A.indptr) and np.array_equal(rt.download(prob.col), A.indices)
+    assert np.array_equal(rt.download(prob.rowptr_t), AT.indptr) and np.array_equal(rt.download(prob.col_t), AT.indices)
+    out_n = g.gauss_newton_krylow(rp.res, x0, rp.jac, callback=lambda **kw: None)
+    monkeypatch.setenv("GNK_NATIVE_ROSENBROCK", "0")
+    out_h = g.gauss_newton_krylow(rp.res, x0, rp.jac, callback=lambda **kw: None)
+    assert (out_n.nit, out_n.nrev, out_n.njev) == (out_h.nit, out_h.nrev, out_h.njev) == (48, 49, 48)
+    assert np.array_equal(out_n.x, out_h.x)
+
+
 def test_rosenbrock_3d_dense_jacobian(g):
     """rosenbrock_3d_test.py: p = 2, dense J -> direct least squares; Armijo halving is exercised (71 evaluations)."""
     import scipy.sparse
