@@ -75,6 +75,7 @@ SIGNATURES = {
     "gnk_comm_p2p_attach": (_I, [_P, _P]),
     "gnk_comm_p2p_enabled": (_I, [_P]),
     "gnk_comm_p2p_disable": (_I, [_P]),
+    "gnk_comm_fused_reductions": (_I, [_P]),
     "gnk_comm_allreduce": (_I, [_P, _P, _I, _I, _P]),
     "gnk_comm_halo_exchange": (_I, [_P, _LP, _P, _I, _P]),
     "gnk_comm_allgather_owned": (_I, [_P, _LP, _P, _P, C.POINTER(_L), _P]),

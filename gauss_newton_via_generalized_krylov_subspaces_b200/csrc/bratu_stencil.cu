@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_brat
                                                          const double* __restrict__ y, double* __restrict__ F,
                                                          double* __restrict__ expu, int depth, int TR,
                                                          double* __restrict__ partials, unsigned int* ticket,
-                                                         double* __restrict__ loss) {
+                                                         double* __restrict__ loss, gnk_p2p_dev pd) {
   __shared__ double sh[32];
   constexpr int W = VEC ? 2 : 1;
   const int m = lay.m;
@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_brat
     for (unsigned int i = threadIdx.x; i < nb; i += blockDim.x) a += __ldcg(partials + i);
     a = block_sum(a, sh);
     if (threadIdx.x == 0) loss[0] = a;
+    if (pd.peers) {  // sum over the ranks, in this CTA, over the peers' mailboxes
+      __syncthreads();
+      p2p_tail_allreduce(pd, loss, 1, 0);
+    }
   }
 }
 
@@ -397,12 +401,13 @@ int gnk_bratu_residual(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm
   dim3 grid(gx, (unsigned)ceil_div(R, tr));
   GNK_REQUIRE((int64_t)grid.x * grid.y <= 65536, "gnk_bratu_residual: grid exceeds the partials scratch");
   double* part = ctx->d_partials + PART_RESID;
+  const gnk_p2p_dev pd = p2p_next(ctx);
   if (vec)
     residual_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, d_u, d_y, d_F, d_expu, depth, tr, part,
-                                                                 ctx->d_tickets + TK_RESID, d_loss);
+                                                                 ctx->d_tickets + TK_RESID, d_loss, pd);
   else
     residual_kernel<false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, d_u, d_y, d_F, d_expu, depth, tr, part,
-                                                                  ctx->d_tickets + TK_RESID, d_loss);
+                                                                  ctx->d_tickets + TK_RESID, d_loss, pd);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

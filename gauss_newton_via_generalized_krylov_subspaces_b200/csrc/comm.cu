@@ -110,49 +110,10 @@ int ensure_gather(gnk_ctx* ctx, size_t bytes, cudaStream_t st) {
 // Slots are double-buffered on the parity of the sequence number: a rank can be at most one collective ahead of a
 // peer (it cannot finish collective s without the peer's flag s), so slot parity s is never overwritten before the
 // peer has left collective s-2.  Results are bitwise identical on all ranks (same rank-ordered reduction).
-// Mailbox layout (bytes): [0, 4096) flags: u64 gather[16], u64 halo[2] at +1024;
-//                         gather data 2 x nranks x P2P_GMAX doubles; halo data 2 parities x 2 sides x P2P_HMAX doubles.
+// The residual, Gram-Schmidt dots and update-statistics kernels run the same protocol in their own last CTA
+// (p2p_tail_allreduce, common.cuh), so those reductions need no kernel of their own at all.
 // =================================================================================================
-constexpr int P2P_MAXR = 16;
-constexpr int64_t P2P_GMAX = (int64_t)GNK_MAX_BASIS * GNK_MAX_BASIS;  // largest gather: one R triangle
-constexpr int64_t P2P_HMAX = 2 * 16384;                              // largest halo message: 2 grid rows of 16384
-constexpr size_t P2P_FLAG_BYTES = 4096;
-constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
-
-__host__ __device__ inline size_t p2p_gather_off(int nranks, int parity, int r) {
-  return P2P_FLAG_BYTES + sizeof(double) * (size_t)((parity * nranks + r) * P2P_GMAX);
-}
-__host__ __device__ inline size_t p2p_halo_off(int nranks, int parity, int side) {
-  return P2P_FLAG_BYTES + sizeof(double) * (size_t)(2 * nranks * P2P_GMAX) +
-         sizeof(double) * (size_t)((parity * 2 + side) * P2P_HMAX);
-}
 inline size_t p2p_bytes(int nranks) { return p2p_halo_off(nranks, 2, 0); }
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// spin until *flag >= seq; a peer that never arrives (diverged control flow, dead process) must not hang the GPU
-__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long seq) {
-  const unsigned long long t0 = global_ns();
-  while (ld_acquire_sys(flag) < seq) {
-    if (global_ns() - t0 > P2P_TIMEOUT_NS) __trap();
-  }
-}
-__device__ __forceinline__ double ld_volatile(const double* p) {
-  double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // op: 0 sum, 1 max, 2 (sum, max) pair as in gnk_comm_allreduce, 3 no reduction: out receives the nranks x count stack
 __global__ void __launch_bounds__(1024) p2p_gather_kernel(void* const* __restrict__ peers, int rank, int nranks,
@@ -321,14 +282,16 @@ int gnk_comm_p2p_attach(gnk_ctx* ctx, const void* handles) {
   ctx->p2p_seq = 0;
   ctx->p2p_hseq = 0;
   ctx->p2p_ready = 1;
+  ctx->p2p_fused = !(getenv("GNK_P2P_FUSED") && atoi(getenv("GNK_P2P_FUSED")) == 0);
   return 0;
 }
 
 int gnk_comm_p2p_enabled(gnk_ctx* ctx) { return ctx ? ctx->p2p_ready : 0; }
 int gnk_comm_p2p_disable(gnk_ctx* ctx) {
-  if (ctx) ctx->p2p_ready = 0;
+  if (ctx) ctx->p2p_ready = ctx->p2p_fused = 0;
   return 0;
 }
+int gnk_comm_fused_reductions(gnk_ctx* ctx) { return (ctx && ctx->p2p_ready && ctx->p2p_fused) ? 1 : 0; }
 
 int gnk_comm_size(gnk_ctx* ctx) { return ctx ? ctx->nranks : 0; }
 

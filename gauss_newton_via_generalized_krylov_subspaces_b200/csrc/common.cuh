@@ -35,6 +35,7 @@ struct gnk_ctx {
   unsigned long long p2p_seq = 0;     // gathers issued so far (identical on all ranks: same call sequence)
   unsigned long long p2p_hseq = 0;    // halo exchanges issued so far
   int p2p_ready = 0;
+  int p2p_fused = 0;                  // the reducing kernels finish their cross-rank reduction themselves
   // per-CTA partial dot products of gnk_stencil_apply_dots (k * CTAs-per-column doubles, grown on demand)
   double* d_apart = nullptr;
   size_t apart_bytes = 0;
@@ -138,6 +139,100 @@ __device__ __forceinline__ unsigned int linear_block_id() {
   return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
 }
 __device__ __forceinline__ unsigned int total_blocks() { return gridDim.x * gridDim.y * gridDim.z; }
+
+// ------------------------------------------------------------------------------------------------
+// peer-memory mailboxes (comm.cu): layout and the device side of a gather, shared with the kernels that finish their
+// cross-rank reduction in their own last CTA (residual, Gram-Schmidt dots, update statistics)
+// Mailbox layout (bytes): [0, 4096) flags: u64 gather[16], u64 halo[2] at +1024;
+//                         gather data 2 x nranks x P2P_GMAX doubles; halo data 2 parities x 2 sides x P2P_HMAX doubles.
+// ------------------------------------------------------------------------------------------------
+constexpr int P2P_MAXR = 16;
+constexpr int64_t P2P_GMAX = (int64_t)GNK_MAX_BASIS * GNK_MAX_BASIS;  // largest gather: one R triangle
+constexpr int64_t P2P_HMAX = 2 * 16384;                              // largest halo message: 2 grid rows of 16384
+constexpr size_t P2P_FLAG_BYTES = 4096;
+constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+__host__ __device__ inline size_t p2p_gather_off(int nranks, int parity, int r) {
+  return P2P_FLAG_BYTES + sizeof(double) * (size_t)((parity * nranks + r) * P2P_GMAX);
+}
+__host__ __device__ inline size_t p2p_halo_off(int nranks, int parity, int side) {
+  return P2P_FLAG_BYTES + sizeof(double) * (size_t)(2 * nranks * P2P_GMAX) +
+         sizeof(double) * (size_t)((parity * 2 + side) * P2P_HMAX);
+}
+
+struct gnk_p2p_dev {        // kernel argument; peers == nullptr: single rank or NCCL path, nothing to do
+  void* const* peers;
+  int rank, nranks;
+  unsigned long long seq;
+};
+// the next collective of the gather channel, if the library finishes reductions inside the producing kernels
+static inline gnk_p2p_dev p2p_next(gnk_ctx* ctx) {
+  gnk_p2p_dev pd{nullptr, 0, 1, 0ull};
+  if (ctx->p2p_ready && ctx->p2p_fused) {
+    pd.peers = ctx->d_p2p_peer;
+    pd.rank = ctx->rank;
+    pd.nranks = ctx->nranks;
+    pd.seq = ++ctx->p2p_seq;
+  }
+  return pd;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= seq; a peer that never arrives (diverged control flow, dead process) must not hang the GPU
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long seq) {
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < seq) {
+    if (global_ns() - t0 > P2P_TIMEOUT_NS) __trap();
+  }
+}
+__device__ __forceinline__ double ld_volatile(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Cross-rank reduction of vals[0..count) (count, nranks <= blockDim.x), executed by ALL threads of ONE CTA -- the
+// CTA that has just written this rank's values (make them visible with a __syncthreads first).  Same protocol and
+// same rank-ordered arithmetic as p2p_gather_kernel (comm.cu): store into every peer's mailbox over NVLink, fence,
+// raise the flags, wait for the peers' flags, reduce out of local memory.  op: 0 sum, 1 max, 2 (sum, max) pair.
+__device__ __forceinline__ void p2p_tail_allreduce(const gnk_p2p_dev& pd, double* vals, int count, int op) {
+  const int t = threadIdx.x;
+  const int parity = (int)(pd.seq & 1ull);
+  if (t < count) {
+    const double v = vals[t];
+    for (int r = 0; r < pd.nranks; ++r)
+      reinterpret_cast<double*>(static_cast<char*>(pd.peers[r]) + p2p_gather_off(pd.nranks, parity, pd.rank))[t] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  char* mine = static_cast<char*>(pd.peers[pd.rank]);
+  if (t < pd.nranks) {
+    st_release_sys(reinterpret_cast<unsigned long long*>(pd.peers[t]) + pd.rank, pd.seq);
+    wait_flag(reinterpret_cast<const unsigned long long*>(mine) + t, pd.seq);
+  }
+  __syncthreads();
+  if (t < count) {
+    double a = ld_volatile(reinterpret_cast<const double*>(mine + p2p_gather_off(pd.nranks, parity, 0)) + t);
+    const bool is_max = (op == 1) || (op == 2 && t == 1);
+    for (int r = 1; r < pd.nranks; ++r) {
+      const double b = ld_volatile(reinterpret_cast<const double*>(mine + p2p_gather_off(pd.nranks, parity, r)) + t);
+      a = is_max ? fmax(a, b) : a + b;
+    }
+    vals[t] = a;
+  }
+}
 
 // One row of sign * (M v) or sign * (M^T v), M = L + alpha D + lam diag(e^u), in the order scipy uses for
 // J @ V (csr_matvecs, gauss_newton_krylow.py:86) and -J.T @ r (csc_matvec, krylow.py:62): five rounded products

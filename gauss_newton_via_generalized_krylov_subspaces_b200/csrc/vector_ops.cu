@@ -142,7 +142,7 @@ __device__ __forceinline__ void dots_pass(const double* __restrict__ Vb, int64_t
 
 __global__ void __launch_bounds__(TPB, 4) dots_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
                                                     const double* __restrict__ w, double* __restrict__ partials,
-                                                    unsigned int* ticket, double* __restrict__ h) {
+                                                    unsigned int* ticket, double* __restrict__ h, gnk_p2p_dev pd) {
   __shared__ double sh[32];
   for (int jb = 0; jb < k; jb += JB) {
     double acc[JB];
@@ -176,6 +176,10 @@ __global__ void __launch_bounds__(TPB, 4) dots_kernel(const double* __restrict__
       a = warp_sum(a);
       if (lane == 0) h[j] = a;
     }
+    if (pd.peers) {  // sum over the ranks, in this CTA, over the peers' mailboxes
+      __syncthreads();
+      p2p_tail_allreduce(pd, h, k, 0);
+    }
   }
 }
 
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(TPB, 4) dots_kernel(const double* __restrict__
 __global__ void __launch_bounds__(TPB) update_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
                                                       const double* __restrict__ h, double* __restrict__ w,
                                                       double* __restrict__ partials, unsigned int* ticket,
-                                                      double* __restrict__ stats) {
+                                                      double* __restrict__ stats, gnk_p2p_dev pd) {
   __shared__ double coef[GNK_MAX_BASIS];
   __shared__ double sh[32];
   for (int j = threadIdx.x; j < k; j += blockDim.x) coef[j] = h[j];
@@ -245,6 +249,10 @@ __global__ void __launch_bounds__(TPB) update_kernel(const double* __restrict__ 
     if (threadIdx.x == 0) {
       stats[0] = a;
       stats[1] = b;
+    }
+    if (pd.peers) {  // (sum, max) over the ranks, in this CTA, over the peers' mailboxes
+      __syncthreads();
+      p2p_tail_allreduce(pd, stats, 2, 2);
     }
   }
 }
@@ -328,7 +336,8 @@ int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, 
   GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_dots: off/ld must be even");
   int grid = stream_grid(ctx, lay->n_own / 2, 8);
   dots_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V + lay->off, lay->ld, lay->n_own, k, d_w + lay->off,
-                                                      ctx->d_partials + PART_DOTS, ctx->d_tickets + TK_DOTS, d_h);
+                                                      ctx->d_partials + PART_DOTS, ctx->d_tickets + TK_DOTS, d_h,
+                                                      p2p_next(ctx));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -341,7 +350,8 @@ int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k
   int grid = stream_grid(ctx, lay->n_own / 2, 8);
   update_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V + lay->off, lay->ld, lay->n_own, k, d_h,
                                                         d_w + lay->off, ctx->d_partials + PART_UPDATE,
-                                                        ctx->d_tickets + TK_UPDATE, d_stats);
+                                                        ctx->d_tickets + TK_UPDATE, d_stats,
+                                                        d_stats ? p2p_next(ctx) : gnk_p2p_dev{nullptr, 0, 1, 0ull});
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -16,6 +16,7 @@ _runtime = None
 
 
 class Runtime:
+    fused_reductions = False
     def __init__(self):
         import torch
 
@@ -32,6 +33,7 @@ class Runtime:
         _lib.check(self.lib.gnk_create(C.byref(ctx), self.device_index), "gnk_create")
         self.ctx = ctx
         self.rank, self.world = 0, 1
+        self.fused_reductions = False  # gnk_bratu_residual / gnk_cgs_dots / gnk_cgs_update reduce over the ranks themselves
         self._pinned = torch.empty(4096, dtype=torch.float64, pin_memory=True)
         self._pinned_np = self._pinned.numpy()
         self._pinned_i = torch.empty(16, dtype=torch.int32, pin_memory=True)
@@ -72,6 +74,7 @@ class Runtime:
         dist.all_gather_object(ok, int(rc))
         if any(r != 0 for r in ok):  # e.g. no peer access between some pair of devices: everybody stays on NCCL
             lib.gnk_comm_p2p_disable(self.ctx)
+        self.fused_reductions = bool(lib.gnk_comm_fused_reductions(self.ctx))
 
     # -- helpers -----------------------------------------------------------------------------------
     @property

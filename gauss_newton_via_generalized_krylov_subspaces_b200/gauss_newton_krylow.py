@@ -81,7 +81,8 @@ def cgls_dense(rt, JV, ldjv, n_rows, k, y, sign, rtol, out):
 
     def at_times(vec):  # A^T vec = sign * JV^T vec
         _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(lay), ptr(JV), k, ptr(vec), ptr(h), rt.stream), "gnk_cgs_dots")
-        rt.allreduce(h, k, 0)
+        if not rt.fused_reductions:
+            rt.allreduce(h, k, 0)
         return sign * rt.read(h, k)
 
     def a_times(pv):  # t = JV pv (the sign is applied by the caller)

@@ -129,11 +129,13 @@ class GeneralizedKrylowSubspace:
                                                           ptr(self.w), ptr(self.h), rt.stream),
                                "gnk_stencil_apply_dots")
                 did_spmm = True
+                rt.allreduce(self.h, self.k, 0)
             else:
                 with rt.mark("cgs_dots", 8.0 * n * (self.k + 1)):
                     _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.w),
                                                 ptr(self.h), rt.stream), "gnk_cgs_dots")
-            rt.allreduce(self.h, self.k, 0)
+                if not rt.fused_reductions:  # else summed over the ranks inside the kernel (peer mailboxes)
+                    rt.allreduce(self.h, self.k, 0)
             if spmm is not None and not fuse_dots and ipass == self.reorth_passes - 1:
                 jn, JV, ldjv = spmm[:3]
                 d = jn.pb.dev
@@ -142,11 +144,14 @@ class GeneralizedKrylowSubspace:
                                                        ptr(self.V), self.k, ptr(self.h), ptr(self.w), ptr(self.stats),
                                                        -1.0, ptr(JV), ldjv, rt.stream), "gnk_cgs_update_spmm")
                 did_spmm = True
+                stats_reduced = False
             else:
                 with rt.mark("cgs_update", 8.0 * n * (self.k + 2)):
                     _lib.check(lib.gnk_cgs_update(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.h),
                                                   ptr(self.w), ptr(self.stats), rt.stream), "gnk_cgs_update")
-        rt.allreduce(self.stats, 2, 2)
+                stats_reduced = rt.fused_reductions
+        if not stats_reduced:
+            rt.allreduce(self.stats, 2, 2)
         new = self.col(self.k)
         with rt.mark("normalize", 16.0 * n):
             _lib.check(lib.gnk_normalize(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8, ptr(new),

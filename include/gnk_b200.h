@@ -211,6 +211,11 @@ int gnk_comm_p2p_export(gnk_ctx* ctx, void* out_handle64);
 int gnk_comm_p2p_attach(gnk_ctx* ctx, const void* handles /* nranks x 64 bytes */);
 int gnk_comm_p2p_enabled(gnk_ctx* ctx);
 int gnk_comm_p2p_disable(gnk_ctx* ctx); /* back to the NCCL path (all ranks must call it together) */
+/* 1 if, with the mailboxes attached, gnk_bratu_residual (*d_loss), gnk_cgs_dots (d_h) and gnk_cgs_update (d_stats)
+ * deliver the value reduced over ALL ranks: the last CTA of those kernels runs the mailbox protocol itself (one kernel
+ * for the compute step and its collective), so the host must not call gnk_comm_allreduce on their results.
+ * GNK_P2P_FUSED=0 at attach time keeps the reductions as separate single-CTA kernels. */
+int gnk_comm_fused_reductions(gnk_ctx* ctx);
 /* in-place fixed-order sum (op 0) / max (op 1) of `count` <= 256 doubles over all ranks:
  * all-gather followed by the same rank-ordered reduction everywhere (bitwise identical results). */
 int gnk_comm_allreduce(gnk_ctx* ctx, double* d_buf, int count, int op, void* stream);

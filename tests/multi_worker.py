@@ -33,8 +33,11 @@ def main():
     assert rt.world == world and rt.lib.gnk_comm_size(rt.ctx) == world
     p2p = int(rt.lib.gnk_comm_p2p_enabled(rt.ctx))
     assert p2p == (0 if os.environ.get("GNK_P2P", "1") == "0" else 1), "peer-memory mailboxes did not attach"
+    assert rt.fused_reductions == bool(p2p and os.environ.get("GNK_P2P_FUSED", "1") != "0")
     if rank == 0:
-        print(f"[multi] collectives: {'peer-memory mailboxes (CUDA IPC over NVLink)' if p2p else 'NCCL'}", flush=True)
+        fused = int(rt.lib.gnk_comm_fused_reductions(rt.ctx))
+        print(f"[multi] collectives: {'peer-memory mailboxes (CUDA IPC over NVLink)' if p2p else 'NCCL'}"
+              f"{', reductions finished inside the producing kernels' if fused else ''}", flush=True)
 
     def gather_equal(x):
         t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
