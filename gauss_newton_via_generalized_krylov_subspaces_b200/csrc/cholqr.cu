@@ -1,0 +1,507 @@
+// cholqr.cu -- projected least squares  min || sign*A d - y ||  by CholeskyQR2 on the FP64 tensor pipe
+// (second implementation of scipy.linalg.qr + solve_triangular, gauss_newton_krylow.py:30-35, for the large
+// panels of the Bratu runs; the Householder TSQR of tsqr.cu stays the reference implementation and the fallback).
+//
+// Why: Householder QR of a 64 x c tile is a chain of c dependent reflector steps; measured on B200 the warp-autonomous
+// leaf keeps the FP64 pipe 48 % busy (4.19 ms at n = 4096^2, c = 31).  The Gram matrix
+// G = P^T P of the panel P = [sign*A | y] has no dependency chain at all: it is a stream of independent
+// mma.sync.m8n8k4.f64 (DMMA) instructions whose A and B fragments are the SAME registers -- lane (g, t) of a warp holds
+// P[row t][column 8 I + g], which is both the A fragment of block row I and the B fragment of block column I, so
+// every panel element is loaded from HBM exactly once (128-bit loads) and used in NB + 1 DMMAs.
+//
+// Numerics: a single Cholesky factor of G loses cond(P)^2 eps.  CholeskyQR2 (Yamamoto, Nakatsukasa, Yanagisawa,
+// Fukaya 2015) repairs that with a second pass: R1 = chol(G), B = P R1^{-1} (condition number 1 + O(cond^2 eps)),
+// R2 = chol(B^T B), R = R2 R1; for cond(P) < ~1e7 the factor R is as accurate as the Householder one (normwise
+// backward error O(eps)).  B is never stored: pass 2 re-reads the panel, multiplies each 8-row group by
+// T = R1^{-1} with DMMAs whose OUTPUT fragments (lane (g, t): B^T[8 J + g][rows 2t, 2t+1]) are again directly the
+// A/B fragments of the Gram DMMAs.  The factor kernels refuse (sentinel in the result block, see gnk_b200.h) when a
+// Cholesky pivot falls below 1e-12 of its diagonal entry -- near-consistent or rank-deficient systems -- and the host
+// re-issues the solve with the Householder path.
+//
+// Cost per panel row for c <= 32: 20 + 40 DMMAs per 8 rows (2.5 + 5 per row) against ~c^2 dependent DFMAs; two reads
+// of the panel (16 n c bytes).  Multi-GPU: the two c x c Gram matrices are all-gathered and summed in rank order on
+// every rank (bit-identical decisions), replacing the TSQR triangle gather and the tree levels.
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+int gnk_comm_allgather_doubles(gnk_ctx* ctx, const double* d_send, double* d_recv, int64_t count, void* stream);
+
+namespace {
+
+constexpr int GW = 12;          // warps per CTA: one CTA per SM with up to 168 registers per thread
+constexpr int GT = 32 * GW;
+constexpr int CH = 16;          // panel rows per warp and load group (RU groups per step)
+constexpr int TLD = 36;         // leading dimension of T in shared memory (conflict-free fragment reads)
+constexpr int MAXC = 32;        // widest panel (k + 1)
+
+__host__ __device__ constexpr int nblocks(int NB) { return NB * (NB + 1) / 2; }
+__host__ __device__ constexpr int blk_index(int NB, int I, int J) { return I * NB - I * (I - 1) / 2 + (J - I); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+struct PanelSource {
+  const double* A;
+  int64_t lda;
+  const double* y;
+  int k;
+  int64_t n_rows;
+};
+
+__device__ __forceinline__ const double* column_ptr(const PanelSource& s, int col) {
+  return col < s.k ? s.A + (int64_t)col * s.lda : (col == s.k ? s.y : nullptr);
+}
+__device__ __forceinline__ double2 load_pair(const double* p, int64_t r, int64_t limit) {
+  if (p != nullptr && r < limit) return __ldcs(reinterpret_cast<const double2*>(p + r));
+  return make_double2(0.0, 0.0);
+}
+
+// Sum the per-warp fragment accumulators of a CTA in warp order, publish the CTA's partial, and let the CTA that
+// arrives last add the partials of all CTAs in CTA order (deterministic).  NE = doubles per Gram matrix in fragment
+// order: block (I <= J) * 64 + lane * 2 + {0, 1}  <->  G[8 I + g][8 J + 2 t + {0, 1}].
+template <int NBLK>
+__device__ __forceinline__ void reduce_gram(double (&acc)[NBLK][2], double* red, double* __restrict__ partials,
+                                            unsigned int* ticket, double* __restrict__ Gout) {
+  constexpr int NE = NBLK * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int w = 0; w < GW; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        double2* p = reinterpret_cast<double2*>(red + b * 64 + lane * 2);
+        double2 v = make_double2(acc[b][0], acc[b][1]);
+        if (w > 0) {
+          const double2 o = *p;
+          v.x += o.x;
+          v.y += o.y;
+        }
+        *p = v;
+      }
+    }
+    __syncthreads();
+  }
+  double* mine = partials + (int64_t)blockIdx.x * NE;
+  for (int e = threadIdx.x; e < NE; e += GT) mine[e] = red[e];
+  __threadfence();  // every thread publishes its own stores before the CTA takes its ticket
+  if (!grid_arrive_last(ticket)) return;
+  const int nb = gridDim.x;
+  for (int e = threadIdx.x; e < NE; e += GT) {
+    double s = 0.0;
+    int b = 0;
+    for (; b + 4 <= nb; b += 4) {
+      const double v0 = __ldcg(partials + (int64_t)(b + 0) * NE + e);
+      const double v1 = __ldcg(partials + (int64_t)(b + 1) * NE + e);
+      const double v2 = __ldcg(partials + (int64_t)(b + 2) * NE + e);
+      const double v3 = __ldcg(partials + (int64_t)(b + 3) * NE + e);
+      s = (((s + v0) + v1) + v2) + v3;
+    }
+    for (; b < nb; ++b) s += __ldcg(partials + (int64_t)b * NE + e);
+    Gout[e] = s;
+  }
+}
+
+// ---- pass 1: G = P^T P --------------------------------------------------------------------------------------------
+template <int NB, int RU>
+struct GramTile {
+  double2 v[NB][2 * RU];  // [column block][8-row group]: rows r0 + 8 h + 2 t + {0, 1} of column 8 I + g
+};
+
+template <int NB, int RU>
+__device__ __forceinline__ void gram_load(GramTile<NB, RU>& T, const double* const (&cp)[NB], int64_t r0,
+                                          int64_t limit, int t) {
+#pragma unroll
+  for (int I = 0; I < NB; ++I)
+#pragma unroll
+    for (int h = 0; h < 2 * RU; ++h) T.v[I][h] = load_pair(cp[I], r0 + 8 * h + 2 * t, limit);
+}
+template <int NB, int RU>
+__device__ __forceinline__ void gram_accumulate(const GramTile<NB, RU>& T, double (&acc)[nblocks(NB)][2]) {
+#pragma unroll
+  for (int h = 0; h < 2 * RU; ++h)
+#pragma unroll
+    for (int I = 0; I < NB; ++I)
+#pragma unroll
+      for (int J = I; J < NB; ++J) {
+        const int b = blk_index(NB, I, J);
+        dmma(acc[b][0], acc[b][1], T.v[I][h].x, T.v[J][h].x);
+        dmma(acc[b][0], acc[b][1], T.v[I][h].y, T.v[J][h].y);
+      }
+}
+
+template <int NB, int RU>
+__global__ void __launch_bounds__(GT, 1)
+    cholqr_gram_kernel(PanelSource src, int64_t rows_per_cta, double* __restrict__ partials, unsigned int* ticket,
+                       double* __restrict__ Gout) {
+  constexpr int NBLK = nblocks(NB);
+  __shared__ __align__(16) double red[NBLK * 64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const double* cp[NB];
+#pragma unroll
+  for (int I = 0; I < NB; ++I) cp[I] = column_ptr(src, 8 * I + g);
+  double acc[NBLK][2];
+#pragma unroll
+  for (int b = 0; b < NBLK; ++b) acc[b][0] = acc[b][1] = 0.0;
+
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t limit = row0 + rows_per_cta;
+  if (limit > src.n_rows) limit = src.n_rows;
+  constexpr int64_t STRIDE = (int64_t)CH * RU * GW;
+  int64_t r = row0 + (int64_t)warp * (CH * RU);
+  GramTile<NB, RU> ta, tb;
+  gram_load(ta, cp, r, limit, t);
+  while (r < limit) {
+    gram_load(tb, cp, r + STRIDE, limit, t);
+    gram_accumulate(ta, acc);
+    r += STRIDE;
+    if (r >= limit) break;
+    gram_load(ta, cp, r + STRIDE, limit, t);
+    gram_accumulate(tb, acc);
+    r += STRIDE;
+  }
+  reduce_gram<NBLK>(acc, red, partials, ticket, Gout);
+}
+
+// ---- pass 2: G2 = B^T B with B = P T formed on the fly ---------------------------------------------------------------
+template <int NB, int RU>
+struct RowTile {
+  double2 v[RU][2 * NB];  // [16-row group u][4-column chunk I']: rows r0 + 16 u + 2 g + {0, 1} of column 4 I' + t
+};
+template <int NB, int RU>
+__device__ __forceinline__ void row_load(RowTile<NB, RU>& T, const PanelSource& s, int64_t r0, int64_t limit, int g,
+                                         int t) {
+#pragma unroll
+  for (int Ip = 0; Ip < 2 * NB; ++Ip) {
+    const double* p = column_ptr(s, 4 * Ip + t);
+#pragma unroll
+    for (int u = 0; u < RU; ++u) T.v[u][Ip] = load_pair(p, r0 + 16 * u + 2 * g, limit);
+  }
+}
+// one group of 8 panel rows (the .x or the .y halves of a RowTile): B^T = T^T P^T block by block, then B^T B
+template <int NB>
+__device__ __forceinline__ void row_group(const double (&p)[2 * NB], const double* __restrict__ Ts, int g, int t,
+                                          double (&acc)[nblocks(NB)][2]) {
+  double bt[NB][2];
+#pragma unroll
+  for (int J = 0; J < NB; ++J) {
+    bt[J][0] = bt[J][1] = 0.0;
+#pragma unroll
+    for (int Ip = 0; Ip < 2 * NB; ++Ip) {
+      if (Ip <= 2 * J + 1) {  // T is upper triangular: rows 4 I' .. 4 I' + 3 reach block column J only if 4 I' <= 8 J + 7
+        const double a = Ts[(4 * Ip + t) * TLD + 8 * J + g];
+        dmma(bt[J][0], bt[J][1], a, p[Ip]);
+      }
+    }
+  }
+#pragma unroll
+  for (int I = 0; I < NB; ++I)
+#pragma unroll
+    for (int J = I; J < NB; ++J) {
+      const int b = blk_index(NB, I, J);
+      dmma(acc[b][0], acc[b][1], bt[I][0], bt[J][0]);
+      dmma(acc[b][0], acc[b][1], bt[I][1], bt[J][1]);
+    }
+}
+template <int NB, int RU>
+__device__ __forceinline__ void row_accumulate(const RowTile<NB, RU>& T, const double* __restrict__ Ts, int g, int t,
+                                               double (&acc)[nblocks(NB)][2]) {
+  double p[2 * NB];
+#pragma unroll
+  for (int u = 0; u < RU; ++u) {
+#pragma unroll
+    for (int Ip = 0; Ip < 2 * NB; ++Ip) p[Ip] = T.v[u][Ip].x;
+    row_group<NB>(p, Ts, g, t, acc);
+#pragma unroll
+    for (int Ip = 0; Ip < 2 * NB; ++Ip) p[Ip] = T.v[u][Ip].y;
+    row_group<NB>(p, Ts, g, t, acc);
+  }
+}
+
+template <int NB, int RU>
+__global__ void __launch_bounds__(GT, 1)
+    cholqr_gram2_kernel(PanelSource src, int64_t rows_per_cta, const double* __restrict__ Tg,
+                        const int* __restrict__ status, double* __restrict__ partials, unsigned int* ticket,
+                        double* __restrict__ Gout) {
+  constexpr int NBLK = nblocks(NB);
+  __shared__ __align__(16) double red[NBLK * 64];
+  __shared__ __align__(16) double Ts[MAXC * TLD];
+  if (*status != 0) return;  // pass 1 refused: the factor kernel reports it (uniform across the grid)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int e = threadIdx.x; e < MAXC * TLD; e += GT) Ts[e] = Tg[e];
+  __syncthreads();
+  double acc[NBLK][2];
+#pragma unroll
+  for (int b = 0; b < NBLK; ++b) acc[b][0] = acc[b][1] = 0.0;
+
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t limit = row0 + rows_per_cta;
+  if (limit > src.n_rows) limit = src.n_rows;
+  constexpr int64_t STRIDE = (int64_t)CH * RU * GW;
+  int64_t r = row0 + (int64_t)warp * (CH * RU);
+  RowTile<NB, RU> ta, tb;
+  row_load(ta, src, r, limit, g, t);
+  while (r < limit) {
+    row_load(tb, src, r + STRIDE, limit, g, t);
+    row_accumulate(ta, Ts, g, t, acc);
+    r += STRIDE;
+    if (r >= limit) break;
+    row_load(ta, src, r + STRIDE, limit, g, t);
+    row_accumulate(tb, Ts, g, t, acc);
+    r += STRIDE;
+  }
+  reduce_gram<NBLK>(acc, red, partials, ticket, Gout);
+}
+
+// ---- the small factorisations (one warp) -------------------------------------------------------------------------------
+constexpr int GLD = MAXC + 1;
+constexpr double PIVOT_FLOOR_1 = 1e-12;  // pass 1: reduced pivot / diagonal entry ~ 1 / cond^2 of the leading columns
+constexpr double PIVOT_FLOOR_2 = 0.25;   // pass 2: G2 = I + O(cond^2 eps)
+
+// Gs (c x c, upper part valid) -> upper Cholesky factor in place (G = R^T R).  Returns false (in every lane) when a
+// pivot is not safely positive.  One warp; lane = column.
+__device__ bool warp_cholesky(double* Gs, int c, double floor_rel, int lane) {
+  bool ok = true;
+  const double dl = (lane < c) ? Gs[lane * GLD + lane] : 1.0;  // original diagonal of my column
+  for (int j = 0; j < c; ++j) {
+    const double ajj = Gs[j * GLD + j];
+    const double dj = __shfl_sync(0xffffffffu, dl, j);
+    if (!(ajj > floor_rel * dj) || !(dj > 0.0)) {
+      ok = false;
+      break;  // uniform: every lane reads the same values
+    }
+    const double piv = sqrt(ajj);
+    double rjl = 0.0;
+    if (lane >= j && lane < c) {
+      rjl = (lane == j) ? piv : Gs[j * GLD + lane] / piv;
+      Gs[j * GLD + lane] = rjl;
+    }
+    __syncwarp();
+    if (lane > j && lane < c) {
+      for (int i = j + 1; i <= lane; ++i) Gs[i * GLD + lane] = fma(-Gs[j * GLD + i], rjl, Gs[i * GLD + lane]);
+    }
+    __syncwarp();
+  }
+  return ok;
+}
+
+// gather the Gram matrix from fragment order into Gs (upper part), adding the ranks' contributions in rank order
+__device__ void gather_gram(const double* __restrict__ parts, int nparts, int NB, int c, double* Gs) {
+  const int NE = nblocks(NB) * 64;
+  for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+    double s = parts[e];
+    for (int r = 1; r < nparts; ++r) s += parts[(int64_t)r * NE + e];
+    const int b = e >> 6, lane = (e >> 1) & 31, v = e & 1;
+    int I = 0, rem = b;
+    while (rem >= NB - I) {
+      rem -= NB - I;
+      ++I;
+    }
+    const int J = I + rem;
+    const int row = 8 * I + (lane >> 2), col = 8 * J + 2 * (lane & 3) + v;
+    if (row < c && col < c && row <= col) Gs[row * GLD + col] = s;
+  }
+}
+
+// Result block of a refused solve: d = 0 (the trial the host has already queued evaluates the unchanged iterate),
+// rank-deficiency count -1 = "re-issue with the Householder path" (gnk_b200.h).
+__device__ void write_refusal(int k, double* out) {
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    out[i] = 0.0;
+    out[k + 4 + i] = 1.0;
+  }
+  if (threadIdx.x == 0) {
+    out[k] = 0.0;
+    out[k + 1] = 0.0;
+    out[k + 2] = -1.0;
+    out[k + 3] = 0.0;
+  }
+}
+
+// phase 1: R1 = chol(G), T = R1^{-1} with the sign of the A columns folded in (rows i < k of T scaled by sign).
+__global__ void __launch_bounds__(128) cholqr_factor1_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
+                                                             double sign, double* __restrict__ Tg,
+                                                             double* __restrict__ R1g, int* __restrict__ status) {
+  __shared__ double Gs[MAXC * GLD];
+  __shared__ double Tsm[MAXC * GLD];
+  const int c = k + 1;
+  const int lane = threadIdx.x & 31;
+  for (int e = threadIdx.x; e < MAXC * GLD; e += blockDim.x) {
+    Gs[e] = 0.0;
+    Tsm[e] = 0.0;
+  }
+  __syncthreads();
+  gather_gram(parts, nparts, NB, c, Gs);
+  __syncthreads();
+  if (threadIdx.x < k) Gs[threadIdx.x * GLD + k] *= sign;  // (sign A)^T y
+  __syncthreads();
+  bool ok = true;
+  if (threadIdx.x < 32) {
+    ok = warp_cholesky(Gs, c, PIVOT_FLOOR_1, lane);
+    if (ok && lane < c) {
+      // column `lane` of T = R1^{-1}: back substitution of R1 t = e_lane
+      const int j = lane;
+      Tsm[j * GLD + j] = 1.0 / Gs[j * GLD + j];
+      for (int i = j - 1; i >= 0; --i) {
+        double s = 0.0;
+        for (int l = i + 1; l <= j; ++l) s = fma(Gs[i * GLD + l], Tsm[l * GLD + j], s);
+        Tsm[i * GLD + j] = -s / Gs[i * GLD + i];
+      }
+    }
+  }
+  __shared__ int ok_sh;
+  if (threadIdx.x == 0) {
+    ok_sh = ok ? 1 : 0;
+    *status = ok ? 0 : 1;
+  }
+  __syncthreads();
+  const bool good = ok_sh != 0;
+  for (int e = threadIdx.x; e < MAXC * TLD; e += blockDim.x) {
+    const int i = e / TLD, j = e - i * TLD;
+    double v = 0.0;
+    if (good && i < c && j < c && i <= j) v = Tsm[i * GLD + j] * (i < k ? sign : 1.0);
+    Tg[e] = v;
+  }
+  for (int e = threadIdx.x; e < MAXC * MAXC; e += blockDim.x) {
+    const int i = e / MAXC, j = e - i * MAXC;
+    R1g[e] = (good && i < c && j < c && i <= j) ? Gs[i * GLD + j] : 0.0;
+  }
+}
+
+// phase 2: R2 = chol(G2), R = R2 R1, back substitution and the scalar block of gnk_tsqr_ls.
+__global__ void __launch_bounds__(128) cholqr_factor2_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
+                                                             const double* __restrict__ R1g,
+                                                             const int* __restrict__ status, double* __restrict__ out) {
+  __shared__ double Gs[MAXC * GLD];
+  __shared__ double Rs[MAXC * GLD];
+  __shared__ double R1s[MAXC * GLD];
+  __shared__ double dsh[MAXC];
+  __shared__ int ok_sh;
+  const int c = k + 1;
+  const int lane = threadIdx.x & 31;
+  if (*status != 0) {
+    write_refusal(k, out);
+    return;
+  }
+  for (int e = threadIdx.x; e < MAXC * GLD; e += blockDim.x) {
+    Gs[e] = 0.0;
+    Rs[e] = 0.0;
+  }
+  for (int e = threadIdx.x; e < MAXC * MAXC; e += blockDim.x) R1s[(e / MAXC) * GLD + (e % MAXC)] = R1g[e];
+  __syncthreads();
+  gather_gram(parts, nparts, NB, c, Gs);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const bool ok = warp_cholesky(Gs, c, PIVOT_FLOOR_2, lane);
+    if (lane == 0) ok_sh = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (!ok_sh) {
+    write_refusal(k, out);
+    return;
+  }
+  // R = R2 R1 (upper x upper), ascending l
+  for (int e = threadIdx.x; e < c * c; e += blockDim.x) {
+    const int i = e / c, j = e - i * c;
+    if (i <= j) {
+      double s = 0.0;
+      for (int l = i; l <= j; ++l) s = fma(Gs[i * GLD + l], R1s[l * GLD + j], s);
+      Rs[i * GLD + j] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // back substitution R[:k,:k] d = R[:k,k], then the scalars (same block layout as solve_block in tsqr.cu)
+    for (int i = k - 1; i >= 0; --i) {
+      double s = 0.0;
+      for (int j = i + 1 + lane; j < k; j += 32) s = fma(Rs[i * GLD + j], dsh[j], s);
+      s = warp_sum(s);
+      if (lane == 0) dsh[i] = (Rs[i * GLD + k] - s) / Rs[i * GLD + i];
+      __syncwarp();
+    }
+    double z2 = 0.0, d2 = 0.0, ndef = 0.0;
+    for (int i = lane; i < k; i += 32) {
+      const double z = Rs[i * GLD + k], d = dsh[i], rii = Rs[i * GLD + i];
+      z2 = fma(z, z, z2);
+      d2 = fma(d, d, d2);
+      if (fabs(rii) <= 1e-8) ndef += 1.0;
+      out[i] = d;
+      out[k + 4 + i] = rii;
+    }
+    z2 = warp_sum(z2);
+    d2 = warp_sum(d2);
+    ndef = warp_sum(ndef);
+    if (lane == 0) {
+      out[k] = z2;
+      out[k + 1] = Rs[k * GLD + k] * Rs[k * GLD + k];
+      out[k + 2] = ndef;
+      out[k + 3] = d2;
+    }
+  }
+}
+
+// scratch layout inside gnk_ctx::d_cholqr (doubles)
+constexpr int64_t NE_MAX = nblocks(4) * 64;                        // 640
+constexpr int64_t CQ_PART = 0;                                     // per-CTA partials: MAX_CTAS * NE_MAX
+constexpr int64_t CQ_MAX_CTAS = 512;
+constexpr int64_t CQ_LOCAL = CQ_PART + CQ_MAX_CTAS * NE_MAX;       // this rank's Gram matrix
+constexpr int64_t CQ_ALL = CQ_LOCAL + NE_MAX;                      // all ranks' Gram matrices
+constexpr int64_t CQ_T = CQ_ALL + P2P_MAXR * NE_MAX;               // T (MAXC x TLD)
+constexpr int64_t CQ_R1 = CQ_T + MAXC * TLD;                       // R1 (MAXC x MAXC)
+constexpr int64_t CQ_STATUS = CQ_R1 + MAXC * MAXC;                 // int status word
+constexpr int64_t CQ_TOTAL = CQ_STATUS + 8;
+
+template <int NB, int RU>
+int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k, const double* d_y, double sign,
+               double* d_out, cudaStream_t st) {
+  if (!ctx->d_cholqr) {
+    GNK_CUDA(cudaMalloc(&ctx->d_cholqr, sizeof(double) * CQ_TOTAL));
+    GNK_CUDA(cudaMemsetAsync(ctx->d_cholqr, 0, sizeof(double) * CQ_TOTAL, st));
+  }
+  double* base = ctx->d_cholqr;
+  int* status = reinterpret_cast<int*>(base + CQ_STATUS);
+  PanelSource src{d_A, lda, d_y, k, n_rows};
+  constexpr int64_t GRAN = (int64_t)CH * RU * GW;
+  int64_t ctas = ctx->sm_count < CQ_MAX_CTAS ? ctx->sm_count : CQ_MAX_CTAS;
+  if (ctas * GRAN > n_rows) ctas = ceil_div(n_rows, GRAN);
+  const int64_t rows_per_cta = ceil_div(ceil_div(n_rows, ctas), GRAN) * GRAN;
+  ctas = ceil_div(n_rows, rows_per_cta);
+  const int NE = nblocks(NB) * 64;
+  const bool multi = ctx->nranks > 1;
+  GNK_REQUIRE(ctx->nranks <= P2P_MAXR, "cholqr: more ranks than the Gram gather buffer holds");
+  const double* parts = multi ? base + CQ_ALL : base + CQ_LOCAL;
+
+  cholqr_gram_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_PART,
+                                                        ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
+  GNK_LAUNCH_CHECK(ctx);
+  if (multi)
+    if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
+  cholqr_factor1_kernel<<<1, 128, 0, st>>>(parts, ctx->nranks, NB, k, sign, base + CQ_T, base + CQ_R1, status);
+  GNK_LAUNCH_CHECK(ctx);
+  cholqr_gram2_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_T, status, base + CQ_PART,
+                                                         ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
+  GNK_LAUNCH_CHECK(ctx);
+  if (multi)
+    if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
+  cholqr_factor2_kernel<<<1, 128, 0, st>>>(parts, ctx->nranks, NB, k, base + CQ_R1, status, d_out);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace
+
+// Called by gnk_tsqr_ls (tsqr.cu) for the panels this path accepts; returns 1 when the panel is not eligible.
+int gnk_cholqr_try(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k, const double* d_y,
+                   double sign_a, double* d_out, void* stream) {
+  const int c = k + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c <= 16) return run_cholqr<2, 2>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
+  if (c <= 24) return run_cholqr<3, 1>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
+  if (c <= 32) return run_cholqr<4, 1>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
+  return 1;
+}

@@ -39,6 +39,9 @@ struct gnk_ctx {
   // per-CTA partial dot products of gnk_stencil_apply_dots (k * CTAs-per-column doubles, grown on demand)
   double* d_apart = nullptr;
   size_t apart_bytes = 0;
+  // CholeskyQR2 scratch (cholqr.cu): per-CTA Gram partials, the gathered Gram matrices, T, R1, status word
+  double* d_cholqr = nullptr;
+  int ls_method = 0;                  // gnk_tsqr_ls_method: 0 automatic, 1 Householder TSQR only
 };
 
 constexpr int GNK_PARTIALS = 1 << 18;  // doubles (2 MiB)
@@ -54,7 +57,8 @@ constexpr int64_t PART_SCAL = PART_CG + 8192;                       // 64 device
 constexpr int64_t PART_RESID = GNK_PARTIALS - 65536;                // residual kernel: one per CTA
 static_assert(PART_SCAL + 64 <= PART_RESID, "partials scratch overflow");
 
-enum TicketSlot { TK_RESID = 0, TK_STATS = 1, TK_DOTS = 2, TK_UPDATE = 3, TK_DOT1 = 4, TK_CG = 5, TK_APPLY_DOTS = 6 };
+enum TicketSlot { TK_RESID = 0, TK_STATS = 1, TK_DOTS = 2, TK_UPDATE = 3, TK_DOT1 = 4, TK_CG = 5, TK_APPLY_DOTS = 6,
+                  TK_CHOLQR = 7 };
 
 void gnk_set_error(const std::string& s);
 int gnk_fail(const char* what, cudaError_t e, const char* file, int line);

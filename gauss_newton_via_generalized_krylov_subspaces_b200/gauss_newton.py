@@ -142,7 +142,7 @@ def gauss_newton(
             dA = rt.zeros(lda * p)
             for j in range(p):
                 rt.upload(np.ascontiguousarray(dense[:, j]), dA[j * lda:j * lda + n_res])
-            tsqr_solve(rt, dA, lda, n_res, p, F[res_off:], -1.0, blk)
+            tsqr_solve(rt, dA, lda, n_res, p, F[res_off:], -1.0, blk, householder=True)
             d[off:off + p].copy_(blk[:p])
 
         if native_armijo:

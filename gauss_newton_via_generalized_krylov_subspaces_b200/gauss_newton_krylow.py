@@ -47,9 +47,27 @@ def resolve_problem(res, jac, x0, args, native_rosenbrock=False):
     return HostCallableProblem(res, jac, x0, args)
 
 
-def tsqr_solve(rt, A, lda, n_rows, k, y, sign, out):
-    _lib.check(rt.lib.gnk_tsqr_ls(rt.ctx, ptr(A), lda, n_rows, k, ptr(y), float(sign), ptr(out), rt.stream),
-               "gnk_tsqr_ls")
+def tsqr_solve(rt, A, lda, n_rows, k, y, sign, out, householder=False):
+    """gnk_tsqr_ls.  Large panels are factored by CholeskyQR2 (csrc/cholqr.cu), which refuses numerically rank
+    deficient panels by writing d = 0 and out[k+2] = -1 (``ls_refused``); the caller then comes back with
+    ``householder=True``, which pins the Householder TSQR for this call."""
+    prev = rt.lib.gnk_tsqr_ls_method(rt.ctx, 1) if householder else 0  # returns the previous setting (>= 0)
+    if prev < 0:
+        _lib.check(prev, "gnk_tsqr_ls_method")
+    try:
+        _lib.check(rt.lib.gnk_tsqr_ls(rt.ctx, ptr(A), lda, n_rows, k, ptr(y), float(sign), ptr(out), rt.stream),
+                   "gnk_tsqr_ls")
+    finally:
+        if householder:
+            rt.lib.gnk_tsqr_ls_method(rt.ctx, prev)
+
+
+def ls_refused(vals, k):
+    return vals[k + 2] < 0
+
+
+class _LeastSquaresRefused(Exception):
+    pass
 
 
 def _report_rank(vals, k):
@@ -146,6 +164,9 @@ def linear_least_squares(A, y):
     out = rt.zeros(2 * _NB + 8)
     tsqr_solve(rt, dA, lda, n, k, dy, 1.0, out)
     vals = rt.read(out, 2 * k + 4)
+    if ls_refused(vals, k):
+        tsqr_solve(rt, dA, lda, n, k, dy, 1.0, out, householder=True)
+        vals = rt.read(out, 2 * k + 4)
     _report_rank(vals, k)
     return vals[:k].copy()
 
@@ -303,10 +324,22 @@ def gauss_newton_krylow(
             with rt.mark("residual", 32.0 * n_res_own):
                 prob.residual(x_trial, F_trial, loss_slot, aux=aux[1])
             state["vals"] = rt.read(blk, _BLK)
+            if ls_solver == "qr" and not fused and ls_refused(state["vals"], k):
+                raise _LeastSquaresRefused()
             return float(state["vals"][_SC_LOSS])
 
-        step_length, nfev_delta = armijo_device(
-            trial_loss, prev_loss, lambda: float(state["vals"][k]), lambda: float(np.sqrt(state["vals"][k + 3])))
+        def line_search():
+            return armijo_device(trial_loss, prev_loss, lambda: float(state["vals"][k]),
+                                 lambda: float(np.sqrt(state["vals"][k + 3])))
+
+        try:
+            step_length, nfev_delta = line_search()
+        except _LeastSquaresRefused:
+            # CholeskyQR2 met a numerically rank deficient panel (d = 0 was written, the trial above evaluated the
+            # unchanged iterate and is not counted): same panel again through the Householder TSQR
+            with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
+                tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk, householder=True)
+            step_length, nfev_delta = line_search()
         nfev += nfev_delta
         vals = state["vals"]
         if ls_solver == "qr":

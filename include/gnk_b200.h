@@ -132,9 +132,18 @@ int gnk_cgs_update_spmm(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* pr
  * (= ||A d||^2, armijo_goldstein.py:50), d_out[k+1] = squared LS residual, d_out[k+2] = number of
  * |R_jj| <= 1e-8 (the "A is rank deficient" prints of :32-34), d_out[k+3] = ||d||^2,
  * d_out[k+4 .. 2k+4) = diag(R).  With a communicator attached the R factors of all ranks are
- * gathered and reduced identically on every rank. */
+ * gathered and reduced identically on every rank.
+ * Large panels (9 <= k+1 <= 32, >= 16384 rows, 16-byte aligned) are factored by CholeskyQR2 on the FP64 tensor pipe
+ * instead (cholqr.cu: two Gram passes, R = R2 R1; same R up to row signs, same result block).  That path REFUSES
+ * panels whose Gram matrix is numerically rank deficient (cond ~> 1e6, e.g. a consistent system): it then writes
+ * d = 0 and d_out[k+2] = -1, and the caller re-issues the call after gnk_tsqr_ls_method(ctx, 1). */
 int gnk_tsqr_ls(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k,
                 const double* d_y, double sign_a, double* d_out, void* stream);
+
+/* Factorisation used by gnk_tsqr_ls: 0 = automatic (CholeskyQR2 where eligible, Householder TSQR otherwise; the
+ * default, GNK_LS_CHOLQR=0 in the environment makes 1 the default), 1 = Householder TSQR only.  Returns the previous
+ * setting, or a negative status. */
+int gnk_tsqr_ls_method(gnk_ctx* ctx, int method);
 
 /* Fused form of gnk_stencil_apply + gnk_tsqr_ls for the Bratu stencil: the panel [sign_a * (J V_k) | r] is formed on
  * the fly from the basis columns inside the TSQR leaf (tiles are 8 x 32 blocks of the grid staged with a one-cell

@@ -213,6 +213,11 @@ class MockLib:
         o[k + 4:2 * k + 4] = np.diag(R)[:k]
         return 0
 
+    def gnk_tsqr_ls_method(self, ctx, method):
+        prev = getattr(self, "ls_method", 0)
+        self.ls_method = int(method)
+        return prev
+
     def gnk_tsqr_ls_stencil(self, ctx, lay, prm, expu, V, ldv, k, r, sign_a, out, stream):
         lay_o = obj(lay)
         n = lay_o.n_own

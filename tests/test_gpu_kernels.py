@@ -219,6 +219,115 @@ def test_tsqr_warp_autonomous_leaf(g, n, k):
     assert np.array_equal(x, x2)
 
 
+# ------------------------------------------------------------------------------------------------
+# CholeskyQR2 on the FP64 tensor pipe (csrc/cholqr.cu): same entry point, large even-row panels of 9..32 columns
+# ------------------------------------------------------------------------------------------------
+def _raw_ls(g, A, y, sign, householder):
+    """gnk_tsqr_ls on a host panel; returns the 2k+4 result doubles."""
+    _lib, device = _lib_mods()
+    from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve
+    rt = g.get_runtime()
+    n, k = A.shape
+    lda = (n + 15) // 16 * 16
+    dA = rt.zeros(lda * k)
+    for j in range(k):
+        rt.upload(np.ascontiguousarray(A[:, j]), dA[j * lda:j * lda + n])
+    dy = rt.zeros(lda)
+    rt.upload(y, dy[:n])
+    out = rt.zeros(256)
+    tsqr_solve(rt, dA, lda, n, k, dy, sign, out, householder=householder)
+    return rt.read(out, 2 * k + 4).copy()
+
+
+@pytest.mark.parametrize("n,k", [(16384, 8), (16386, 9), (20000, 15), (50002, 16), (65536, 17), (30000, 23),
+                                 (100000, 24), (262144, 31), (1 << 20, 30), (16384 + 190, 12)])
+def test_cholqr2_matches_householder_and_lstsq(g, n, k):
+    """every block count (2, 3, 4 blocks of 8 columns), partial last steps, CTAs without rows; tolerance: both
+    factorisations are backward stable, so d agrees to eps * cond, the scalars to 1e-11 relative."""
+    rs = np.random.RandomState(n + 31 * k)
+    A = rs.normal(size=(n, k)) @ (np.eye(k) + 0.3 * rs.normal(size=(k, k)))
+    A *= np.exp(rs.uniform(-4, 4, size=k))[None, :]          # graded columns: CholeskyQR is scaling invariant
+    y = rs.normal(size=n)
+    cond = np.linalg.cond(A / np.linalg.norm(A, axis=0))
+    for sign in (1.0, -1.0):
+        vc = _raw_ls(g, A, y, sign, householder=False)
+        vh = _raw_ls(g, A, y, sign, householder=True)
+        assert vc[k + 2] == 0 and vh[k + 2] == 0
+        xr = np.linalg.lstsq(sign * A, y, rcond=None)[0]
+        assert rel(vc[:k], xr) < 1e-13 * max(cond, 10.0), (rel(vc[:k], xr), cond)
+        assert rel(vc[:k], vh[:k]) < 1e-13 * max(cond, 10.0)
+        for i in (k, k + 1, k + 3):                            # ||R d||^2, LS residual^2, ||d||^2
+            assert abs(vc[i] - vh[i]) <= 1e-11 * abs(vh[i]), (i, vc[i], vh[i])
+        assert np.allclose(vc[k + 4:], np.abs(vh[k + 4:]), rtol=1e-11)   # Cholesky R has a positive diagonal
+    # run-to-run deterministic (fixed reduction order) and exact under power-of-two scaling
+    assert np.array_equal(_raw_ls(g, A, y, 1.0, False), _raw_ls(g, A, y, 1.0, False))
+    assert np.array_equal(_raw_ls(g, A * 2.0 ** 30, y * 2.0 ** 30, 1.0, False)[:k], _raw_ls(g, A, y, 1.0, False)[:k])
+
+
+def test_cholqr2_moderately_ill_conditioned(g):
+    """cond(A) = 1e5: a single Cholesky pass would lose cond^2 eps = 1e-6; the second pass restores eps * cond."""
+    rs = np.random.RandomState(11)
+    n, k = 40000, 20
+    U, _ = np.linalg.qr(rs.normal(size=(n, k)))
+    W, _ = np.linalg.qr(rs.normal(size=(k, k)))
+    A = (U * np.logspace(0, -5, k)) @ W.T
+    y = rs.normal(size=n)
+    vc = _raw_ls(g, A, y, 1.0, householder=False)
+    vh = _raw_ls(g, A, y, 1.0, householder=True)
+    xr = np.linalg.lstsq(A, y, rcond=None)[0]
+    assert vc[k + 2] == 0
+    assert rel(vc[:k], xr) < 1e-16 * 1e5 * 200, rel(vc[:k], xr)
+    assert rel(vh[:k], xr) < 1e-16 * 1e5 * 200
+    assert abs(vc[k] - vh[k]) <= 1e-10 * vh[k] and abs(vc[k + 1] - vh[k + 1]) <= 1e-10 * vh[k + 1]
+
+
+def test_cholqr2_refuses_and_falls_back(g, capsys):
+    """consistent system (y in range(A)), nearly dependent columns, exactly repeated column: the Gram matrix is
+    numerically singular -> sentinel (d = 0, out[k+2] = -1); the public entry points fall back to Householder."""
+    rs = np.random.RandomState(12)
+    n, k = 20000, 10
+    A = rs.normal(size=(n, k))
+    x0 = rs.normal(size=k)
+    v = _raw_ls(g, A, A @ x0, 1.0, householder=False)
+    assert v[k + 2] == -1 and np.all(v[:k] == 0) and v[k] == 0 and v[k + 3] == 0
+    assert rel(g.linear_least_squares(A, A @ x0), x0) < 1e-12
+    A2 = A.copy()
+    A2[:, 7] = A2[:, 2] + 1e-9 * rs.normal(size=n)
+    y = rs.normal(size=n)
+    assert _raw_ls(g, A2, y, 1.0, householder=False)[k + 2] == -1
+    xh = _raw_ls(g, A2, y, 1.0, householder=True)
+    assert xh[k + 2] == 0 and rel(g.linear_least_squares(A2, y), xh[:k]) == 0.0
+    A3 = A.copy()
+    A3[:, 4] = A3[:, 1]
+    capsys.readouterr()
+    g.linear_least_squares(A3, y)
+    assert capsys.readouterr().out.count("A is rank deficient") == 1
+    # an all-zero panel must refuse as well (no positive pivot), not produce NaNs silently
+    assert _raw_ls(g, np.zeros((16384, 9)), np.zeros(16384), 1.0, householder=False)[9 + 2] == -1
+
+
+def test_cholqr2_norm_preservation_at_benchmark_size(g):
+    """size-independent properties at 4096^2 rows, k = 30: R^T R = M^T M (diag R against the Cholesky factor of the
+    torch-computed Gram matrix), ||Q^T y||^2 + resid^2 = ||y||^2, agreement with the Householder path."""
+    from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve
+    rt = g.get_runtime()
+    n, k = 4096 * 4096, 30
+    A = rt.torch.randn(k * n, dtype=rt.torch.float64, device=rt.device)
+    y = rt.torch.randn(n, dtype=rt.torch.float64, device=rt.device)
+    out = rt.zeros(256)
+    tsqr_solve(rt, A, n, n, k, y, 1.0, out)
+    v = rt.read(out, 2 * k + 4).copy()
+    tsqr_solve(rt, A, n, n, k, y, 1.0, out, householder=True)
+    vh = rt.read(out, 2 * k + 4).copy()
+    M = rt.torch.cat([A.view(k, n), y.view(1, n)], 0)
+    Gm = (M @ M.T).cpu().numpy()          # torch here is the checker, not the product
+    assert v[k + 2] == 0
+    assert rel(v[:k], vh[:k]) < 1e-12
+    assert abs(v[k] + v[k + 1] - Gm[k, k]) < 1e-12 * Gm[k, k]
+    assert np.allclose(v[k + 4:] ** 2, np.diag(np.linalg.cholesky(Gm[:k, :k])) ** 2, rtol=1e-10)
+    assert np.allclose(v[k + 4:], np.abs(vh[k + 4:]), rtol=1e-12)
+
+
 def test_tsqr_scalar_block_and_rank_deficiency(g, capsys):
     _lib, device = _lib_mods()
     from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve

@@ -122,6 +122,54 @@ def test_host_gnk_bratu(g, capsys):
     assert "reached maximal iteration bound" in capsys.readouterr().out
 
 
+def test_host_gnk_least_squares_refusal_falls_back_to_householder(g):
+    """gnk_tsqr_ls may refuse a panel (CholeskyQR2 on a numerically rank deficient Gram matrix: d = 0 and
+    out[k+2] = -1, include/gnk_b200.h).  The solver must re-issue the SAME solve with the Householder path pinned,
+    not count the wasted trial, and end on the same trajectory."""
+    import ctypes as C
+    gd = Golden("bratu_g101")
+    pb = g.BratuPdeProblem(101, 5, 10)
+    res, jac = pb.make_res(gd["y"]), pb.make_jac()
+    base = g.gauss_newton_krylow(res, gd["u0"], jac, callback=lambda **kw: None, max_iter=12)
+
+    lib = g.get_runtime().lib
+    real = lib.gnk_tsqr_ls
+    calls = {"refused": 0, "householder": 0}
+
+    def refusing(ctx, A, lda, n_rows, k, y, sign_a, out, stream):
+        if getattr(lib, "ls_method", 0) == 0 and k in (3, 4, 9):
+            calls["refused"] += 1
+            o = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(2 * k + 4,))
+            o[:] = 0.0
+            o[k + 2] = -1.0
+            o[k + 4:] = 1.0
+            return 0
+        if getattr(lib, "ls_method", 0) == 1:
+            calls["householder"] += 1
+        return real(ctx, A, lda, n_rows, k, y, sign_a, out, stream)
+
+    lib.gnk_tsqr_ls = refusing
+    try:
+        seen = []
+        out = g.gauss_newton_krylow(res, gd["u0"], jac, callback=lambda x, nfev, cg_iter: seen.append(nfev),
+                                    max_iter=12)
+    finally:
+        lib.gnk_tsqr_ls = real
+    assert calls == {"refused": 3, "householder": 3}
+    assert getattr(lib, "ls_method", 0) == 0                       # the pin is released after the call
+    assert out.nit == base.nit and out.nrev == base.nrev and seen == list(range(2, 13))
+    assert np.array_equal(out.x, base.x)
+    # the public linear_least_squares mirror falls back the same way
+    rs = np.random.RandomState(0)
+    A, y = rs.normal(size=(50, 3)), rs.normal(size=50)
+    lib.gnk_tsqr_ls = refusing
+    try:
+        x = g.linear_least_squares(A, y)
+    finally:
+        lib.gnk_tsqr_ls = real
+    assert rel(x, np.linalg.lstsq(A, y, rcond=None)[0]) < 1e-13
+
+
 def test_host_gn_and_foreign_callables(g):
     from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
     gd = Golden("rosenbrock")

@@ -96,6 +96,10 @@ def main():
             d.apply(E, V, ld, k, -1.0, 0, JV, n, 0)
             report("tsqr", k, timeit(lambda: tsqr_solve(rt, JV, n, n, k, F[d.fields["off"]:], -1.0, blk)),
                    8.0 * n * (k + 1))
+        if want("tsqr_hh"):  # the Householder TSQR pinned (gnk_tsqr_ls_method = 1) beside the default path
+            d.apply(E, V, ld, k, -1.0, 0, JV, n, 0)
+            report("tsqr_hh", k, timeit(lambda: tsqr_solve(rt, JV, n, n, k, F[d.fields["off"]:], -1.0, blk,
+                                                           householder=True)), 8.0 * n * (k + 1))
         if want("combine"):
             report("combine", k, timeit(lambda: lib.gnk_combine(rt.ctx, lay, ptr(V), k, ptr(cc), ptr(dd), 1.0, ptr(x),
                                                                 rt.stream)), 8.0 * n * (k + 1))
