@@ -213,7 +213,7 @@ def run_ours(a):
         kernels[name] = dict(launches=p["launches"], ms=round(p["ms"], 3), achieved_gbs=round(gbs, 1),
                              frac=round(gbs / peak, 3), bytes_per_launch=p["bytes"] / max(p["launches"], 1))
     # measured DRAM traffic per algorithmic byte from the committed ncu --set full captures (profiles/)
-    ncu_name = dict(tsqr="tsqr_quad_kernel", spmm="apply_kernel", combine="combine_kernel", cgs_dots="dots_kernel",
+    ncu_name = dict(tsqr="cholqr", spmm="apply_kernel", combine="combine_kernel", cgs_dots="dots_kernel",
                     cgs_update="update_kernel", residual="residual_kernel")
     try:
         dram = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
@@ -230,22 +230,37 @@ def run_ours(a):
                         share_of_step=round(prof[top]["ms"] / sum(p["ms"] for p in prof.values()), 3),
                         traffic_source="dram__bytes_read+write per algorithmic byte at k=30 (profiles/r01_dram_traffic.json)"
                                        " x this run's bytes per launch",
-                        note="the TSQR leaf reads its panel exactly once but is bound by the FP64 pipe, not by HBM, for "
-                             "k >~ 6 (DESIGN.md section 3): see `fp64`; the streaming kernels are the HBM-bound ones, "
-                             "see `kernels`"
+                        note="the projected least squares (CholeskyQR2, two reads of the panel) is bound by the FP64 "
+                             "tensor pipe for k+1 > 16 and by HBM below (DESIGN.md section 3): see `fp64`; `achieved` "
+                             "counts the panel once (algorithmic bytes); the streaming kernels are in `kernels`"
                         if top == "tsqr" else None)
         if top == "tsqr":
-            # Householder flops of the projected least squares of this step: 2 n (k+1)^2 per outer iteration (k = 1..nit)
+            # FP64 work of the projected least squares of this step (k = 1..nit): panels of 9..32 columns run
+            # CholeskyQR2 as DMMAs (csrc/cholqr.cu: per 8 rows 2 per Gram block in pass 1, the T multiplication plus
+            # 2 per block in pass 2; 512 flops each, padding to blocks of 8 columns included = executed flops);
+            # narrower panels the Householder leaf (2 n (k+1)^2 useful flops)
             try:
                 fpk = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))["fp64_dfma_tflops"]
             except Exception:
                 fpk = 34.2
             n_own = pb.dev.fields["n_own"]
-            flops = sum(2.0 * n_own * (kk + 1) ** 2 for kk in range(1, nit + 1))
+
+            def ls_flops(kk):
+                c = kk + 1
+                if c < 9 or c > 32 or os.environ.get("GNK_LS_CHOLQR", "1") == "0":
+                    return 2.0 * n_own * c * c
+                nb = 2 if c <= 16 else (3 if c <= 24 else 4)
+                nblk = nb * (nb + 1) // 2
+                tmul = sum(min(2 * j + 2, 2 * nb) for j in range(nb))
+                return n_own / 8.0 * (4 * nblk + tmul) * 512.0
+
+            flops = sum(ls_flops(kk) for kk in range(1, nit + 1))
             tf = flops / (prof["tsqr"]["ms"] * 1e-3) / 1e12
             roofline["fp64"] = dict(achieved=round(tf, 2), peak=fpk, unit="TFLOP/s", frac=round(tf / fpk, 3),
-                                    peak_source="measured DFMA throughput, profiles/r01_fp64_peak.json",
-                                    flops="sum over k of 2 n (k+1)^2 (Householder QR of the n x (k+1) panel)")
+                                    peak_source="measured DFMA throughput (DMMA shares the pipe at the same rate), "
+                                                "profiles/r01_fp64_peak.json",
+                                    flops="executed: CholeskyQR2 DMMAs x 512 for 9 <= k+1 <= 32, Householder "
+                                          "2 n (k+1)^2 for k+1 <= 8")
 
     # ---- end-to-end leg: host buffers in, host ndarray out ----------------------------------------
     e2e = None

@@ -153,16 +153,38 @@ __global__ void __launch_bounds__(GT, 1)
   if (limit > src.n_rows) limit = src.n_rows;
   constexpr int64_t STRIDE = (int64_t)CH * RU * GW;
   int64_t r = row0 + (int64_t)warp * (CH * RU);
-  GramTile<NB, RU> ta, tb;
-  gram_load(ta, cp, r, limit, t);
-  while (r < limit) {
+  if constexpr (NB <= 3) {
+    // three rotating register tiles: two steps are in flight while the third is multiplied -- with one step in flight
+    // the narrow panels waited on HBM (ncu: long_scoreboard; 4.8 TB/s at NB = 3).  Measured: NB = 3 -5 %, NB = 2 equal
+    GramTile<NB, RU> ta, tb, tc;
+    gram_load(ta, cp, r, limit, t);
     gram_load(tb, cp, r + STRIDE, limit, t);
-    gram_accumulate(ta, acc);
-    r += STRIDE;
-    if (r >= limit) break;
-    gram_load(ta, cp, r + STRIDE, limit, t);
-    gram_accumulate(tb, acc);
-    r += STRIDE;
+    while (r < limit) {
+      gram_load(tc, cp, r + 2 * STRIDE, limit, t);
+      gram_accumulate(ta, acc);
+      r += STRIDE;
+      if (r >= limit) break;
+      gram_load(ta, cp, r + 2 * STRIDE, limit, t);
+      gram_accumulate(tb, acc);
+      r += STRIDE;
+      if (r >= limit) break;
+      gram_load(tb, cp, r + 2 * STRIDE, limit, t);
+      gram_accumulate(tc, acc);
+      r += STRIDE;
+    }
+  } else {
+    // NB = 4 is bound by the tensor pipe and HBM at the same time; a third tile (168 registers) measured 10 % slower
+    GramTile<NB, RU> ta, tb;
+    gram_load(ta, cp, r, limit, t);
+    while (r < limit) {
+      gram_load(tb, cp, r + STRIDE, limit, t);
+      gram_accumulate(ta, acc);
+      r += STRIDE;
+      if (r >= limit) break;
+      gram_load(ta, cp, r + STRIDE, limit, t);
+      gram_accumulate(tb, acc);
+      r += STRIDE;
+    }
   }
   reduce_gram<NBLK>(acc, red, partials, ticket, Gout);
 }
@@ -263,49 +285,79 @@ constexpr int GLD = MAXC + 1;
 constexpr double PIVOT_FLOOR_1 = 1e-12;  // pass 1: reduced pivot / diagonal entry ~ 1 / cond^2 of the leading columns
 constexpr double PIVOT_FLOOR_2 = 0.25;   // pass 2: G2 = I + O(cond^2 eps)
 
-// Gs (c x c, upper part valid) -> upper Cholesky factor in place (G = R^T R).  Returns false (in every lane) when a
-// pivot is not safely positive.  One warp; lane = column.
-__device__ bool warp_cholesky(double* Gs, int c, double floor_rel, int lane) {
+// The small factorisations run in ONE CTA of 32 x 32 threads: thread (i = warp, l = lane) owns matrix entry [i][l].
+// (History: one warp with the matrix in shared memory took 40 us for c = 31 -- a chain of shared-memory round trips;
+// one warp with the matrix in registers and everything unrolled took the same, waiting for 100 KB of straight-line
+// code to arrive from the instruction cache.  Compact loops over a 1024-thread CTA: a few us.)
+constexpr int FT = MAXC * MAXC;
+constexpr int RB = MAXC + 2;  // published row + the reciprocal of its pivot
+
+// Upper Cholesky factor G = R^T R, right-looking.  a: my entry of G (upper part; anything finite elsewhere).  Step j:
+// warp j publishes row j and 1 / a_jj, one barrier, every thread below row j subtracts a_ji * a_jl / a_jj.  The
+// square roots and the divisions R_jl = a_jl / sqrt(a_jj) are all taken after the loop (one latency, not c).
+// Returns R[i][l] in r (zero outside the upper triangle of the leading c x c block); false (uniformly) if a pivot is
+// not safely positive.
+__device__ __forceinline__ bool block_cholesky(double a, int c, double floor_rel, double* rowbuf, double* diag,
+                                               double& r) {
+  const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (i == l) diag[l] = a;  // read after the first barrier
+  double a_pub = 0.0, piv_pub = 1.0;
   bool ok = true;
-  const double dl = (lane < c) ? Gs[lane * GLD + lane] : 1.0;  // original diagonal of my column
   for (int j = 0; j < c; ++j) {
-    const double ajj = Gs[j * GLD + j];
-    const double dj = __shfl_sync(0xffffffffu, dl, j);
-    if (!(ajj > floor_rel * dj) || !(dj > 0.0)) {
+    double* rb = rowbuf + (j & 1) * RB;
+    if (i == j) {
+      const double ajj = __shfl_sync(0xffffffffu, a, j);
+      rb[l] = a;
+      if (l == 0) rb[MAXC] = __drcp_rn(ajj);
+      a_pub = a;
+      piv_pub = ajj;
+    }
+    __syncthreads();
+    const double ajj = rb[j], dj = diag[j];
+    if (!(ajj > floor_rel * dj) || !(dj > 0.0)) {  // every thread reads the same two numbers
       ok = false;
-      break;  // uniform: every lane reads the same values
+      break;
     }
-    const double piv = sqrt(ajj);
-    double rjl = 0.0;
-    if (lane >= j && lane < c) {
-      rjl = (lane == j) ? piv : Gs[j * GLD + lane] / piv;
-      Gs[j * GLD + lane] = rjl;
-    }
-    __syncwarp();
-    if (lane > j && lane < c) {
-      for (int i = j + 1; i <= lane; ++i) Gs[i * GLD + lane] = fma(-Gs[j * GLD + i], rjl, Gs[i * GLD + lane]);
-    }
-    __syncwarp();
+    if (i > j && l >= i) a = fma(-rb[i], rb[l] * rb[MAXC], a);  // the lower triangle stays zero
+  }
+  r = 0.0;
+  if (ok && i < c && l < c && l >= i) {
+    const double piv = sqrt(piv_pub);
+    r = (l == i) ? piv : a_pub / piv;
   }
   return ok;
 }
 
-// gather the Gram matrix from fragment order into Gs (upper part), adding the ranks' contributions in rank order
-__device__ void gather_gram(const double* __restrict__ parts, int nparts, int NB, int c, double* Gs) {
-  const int NE = nblocks(NB) * 64;
-  for (int e = threadIdx.x; e < NE; e += blockDim.x) {
-    double s = parts[e];
-    for (int r = 1; r < nparts; ++r) s += parts[(int64_t)r * NE + e];
-    const int b = e >> 6, lane = (e >> 1) & 31, v = e & 1;
-    int I = 0, rem = b;
-    while (rem >= NB - I) {
-      rem -= NB - I;
-      ++I;
+// T = R^{-1} for the upper triangular R in Rs (row * GLD + column): back substitution with the 32 unit vectors as
+// right-hand sides, thread (i, l) carries entry [i][l] of the running right-hand side.  Returns T[i][l].
+__device__ __forceinline__ double block_tri_inverse(const double* Rs, int c, double* rowbuf) {
+  const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const bool in = (i < c && l < c);
+  const double rinv = in ? 1.0 / Rs[i * GLD + i] : 0.0;
+  double x = (in && i == l) ? 1.0 : 0.0, t = 0.0;
+  for (int m = c - 1; m >= 0; --m) {
+    double* rb = rowbuf + (m & 1) * RB;
+    if (i == m) {
+      t = x * rinv;
+      rb[l] = t;
     }
-    const int J = I + rem;
-    const int row = 8 * I + (lane >> 2), col = 8 * J + 2 * (lane & 3) + v;
-    if (row < c && col < c && row <= col) Gs[row * GLD + col] = s;
+    __syncthreads();
+    if (i < m) x = fma(-Rs[i * GLD + m], rb[l], x);
   }
+  return (in && l >= i) ? t : 0.0;
+}
+
+// the Gram matrix in fragment order (ranks added in rank order) -> my entry [i][l] (upper part; zero elsewhere)
+__device__ __forceinline__ double gather_gram(const double* __restrict__ parts, int nparts, int NB, int c) {
+  const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (!(i <= l && l < c)) return 0.0;
+  const int I = i >> 3, J = l >> 3;
+  const int b = I * NB - I * (I - 1) / 2 + (J - I);
+  const int e = b * 64 + ((i & 7) * 4 + ((l & 7) >> 1)) * 2 + (l & 1);
+  const int NE = nblocks(NB) * 64;
+  double s = parts[e];
+  for (int r = 1; r < nparts; ++r) s += parts[(int64_t)r * NE + e];
+  return s;
 }
 
 // Result block of a refused solve: d = 0 (the trial the host has already queued evaluates the unchanged iterate),
@@ -324,114 +376,81 @@ __device__ void write_refusal(int k, double* out) {
 }
 
 // phase 1: R1 = chol(G), T = R1^{-1} with the sign of the A columns folded in (rows i < k of T scaled by sign).
-__global__ void __launch_bounds__(128) cholqr_factor1_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
-                                                             double sign, double* __restrict__ Tg,
-                                                             double* __restrict__ R1g, int* __restrict__ status) {
-  __shared__ double Gs[MAXC * GLD];
-  __shared__ double Tsm[MAXC * GLD];
+__global__ void __launch_bounds__(FT) cholqr_factor1_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
+                                                            double sign, double* __restrict__ Tg,
+                                                            double* __restrict__ R1g, int* __restrict__ status) {
+  __shared__ double Rs[MAXC * GLD];
+  __shared__ double rowbuf[2 * RB];
+  __shared__ double diag[MAXC];
   const int c = k + 1;
-  const int lane = threadIdx.x & 31;
-  for (int e = threadIdx.x; e < MAXC * GLD; e += blockDim.x) {
-    Gs[e] = 0.0;
-    Tsm[e] = 0.0;
+  const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double a = gather_gram(parts, nparts, NB, c);
+  if (l == k && i < k) a *= sign;  // (sign A)^T y
+  double r;
+  const bool ok = block_cholesky(a, c, PIVOT_FLOOR_1, rowbuf, diag, r);
+  if (threadIdx.x == 0) *status = ok ? 0 : 1;
+  R1g[i * MAXC + l] = ok ? r : 0.0;
+  double t = 0.0;
+  if (ok) {
+    Rs[i * GLD + l] = r;
+    __syncthreads();  // also separates the row buffers of the two loops
+    t = block_tri_inverse(Rs, c, rowbuf);
+    if (i < k) t *= sign;
   }
-  __syncthreads();
-  gather_gram(parts, nparts, NB, c, Gs);
-  __syncthreads();
-  if (threadIdx.x < k) Gs[threadIdx.x * GLD + k] *= sign;  // (sign A)^T y
-  __syncthreads();
-  bool ok = true;
-  if (threadIdx.x < 32) {
-    ok = warp_cholesky(Gs, c, PIVOT_FLOOR_1, lane);
-    if (ok && lane < c) {
-      // column `lane` of T = R1^{-1}: back substitution of R1 t = e_lane
-      const int j = lane;
-      Tsm[j * GLD + j] = 1.0 / Gs[j * GLD + j];
-      for (int i = j - 1; i >= 0; --i) {
-        double s = 0.0;
-        for (int l = i + 1; l <= j; ++l) s = fma(Gs[i * GLD + l], Tsm[l * GLD + j], s);
-        Tsm[i * GLD + j] = -s / Gs[i * GLD + i];
-      }
-    }
-  }
-  __shared__ int ok_sh;
-  if (threadIdx.x == 0) {
-    ok_sh = ok ? 1 : 0;
-    *status = ok ? 0 : 1;
-  }
-  __syncthreads();
-  const bool good = ok_sh != 0;
-  for (int e = threadIdx.x; e < MAXC * TLD; e += blockDim.x) {
-    const int i = e / TLD, j = e - i * TLD;
-    double v = 0.0;
-    if (good && i < c && j < c && i <= j) v = Tsm[i * GLD + j] * (i < k ? sign : 1.0);
-    Tg[e] = v;
-  }
-  for (int e = threadIdx.x; e < MAXC * MAXC; e += blockDim.x) {
-    const int i = e / MAXC, j = e - i * MAXC;
-    R1g[e] = (good && i < c && j < c && i <= j) ? Gs[i * GLD + j] : 0.0;
-  }
+  Tg[i * TLD + l] = t;
+  if (l < TLD - MAXC) Tg[i * TLD + MAXC + l] = 0.0;
 }
 
 // phase 2: R2 = chol(G2), R = R2 R1, back substitution and the scalar block of gnk_tsqr_ls.
-__global__ void __launch_bounds__(128) cholqr_factor2_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
-                                                             const double* __restrict__ R1g,
-                                                             const int* __restrict__ status, double* __restrict__ out) {
-  __shared__ double Gs[MAXC * GLD];
-  __shared__ double Rs[MAXC * GLD];
+__global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
+                                                            const double* __restrict__ R1g,
+                                                            const int* __restrict__ status, double* __restrict__ out) {
+  __shared__ double R2s[MAXC * GLD];
   __shared__ double R1s[MAXC * GLD];
-  __shared__ double dsh[MAXC];
-  __shared__ int ok_sh;
+  __shared__ double Rs[MAXC * GLD];
+  __shared__ double rowbuf[2 * RB];
+  __shared__ double diag[MAXC];
   const int c = k + 1;
-  const int lane = threadIdx.x & 31;
+  const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (*status != 0) {
     write_refusal(k, out);
     return;
   }
-  for (int e = threadIdx.x; e < MAXC * GLD; e += blockDim.x) {
-    Gs[e] = 0.0;
-    Rs[e] = 0.0;
-  }
-  for (int e = threadIdx.x; e < MAXC * MAXC; e += blockDim.x) R1s[(e / MAXC) * GLD + (e % MAXC)] = R1g[e];
-  __syncthreads();
-  gather_gram(parts, nparts, NB, c, Gs);
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const bool ok = warp_cholesky(Gs, c, PIVOT_FLOOR_2, lane);
-    if (lane == 0) ok_sh = ok ? 1 : 0;
-  }
-  __syncthreads();
-  if (!ok_sh) {
+  R1s[i * GLD + l] = R1g[i * MAXC + l];
+  const double a = gather_gram(parts, nparts, NB, c);
+  double r2;
+  if (!block_cholesky(a, c, PIVOT_FLOOR_2, rowbuf, diag, r2)) {
     write_refusal(k, out);
     return;
   }
-  // R = R2 R1 (upper x upper), ascending l
-  for (int e = threadIdx.x; e < c * c; e += blockDim.x) {
-    const int i = e / c, j = e - i * c;
-    if (i <= j) {
-      double s = 0.0;
-      for (int l = i; l <= j; ++l) s = fma(Gs[i * GLD + l], R1s[l * GLD + j], s);
-      Rs[i * GLD + j] = s;
-    }
+  R2s[i * GLD + l] = r2;
+  __syncthreads();
+  {  // R = R2 R1 (upper x upper), ascending inner index
+    double s = 0.0;
+    if (i <= l && l < c)
+      for (int m = i; m <= l; ++m) s = fma(R2s[i * GLD + m], R1s[m * GLD + l], s);
+    Rs[i * GLD + l] = s;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    // back substitution R[:k,:k] d = R[:k,k], then the scalars (same block layout as solve_block in tsqr.cu)
-    for (int i = k - 1; i >= 0; --i) {
-      double s = 0.0;
-      for (int j = i + 1 + lane; j < k; j += 32) s = fma(Rs[i * GLD + j], dsh[j], s);
-      s = warp_sum(s);
-      if (lane == 0) dsh[i] = (Rs[i * GLD + k] - s) / Rs[i * GLD + i];
-      __syncwarp();
+    // back substitution R[:k,:k] d = R[:k,k], lane = row: once d_j is known every row above subtracts R_ij d_j.  The
+    // reciprocals of the diagonal are formed up front, so a step costs two shuffles and two FMAs, no division.
+    const int lane = threadIdx.x;
+    const bool row = lane < k;
+    double z = row ? Rs[lane * GLD + k] : 0.0;
+    const double rii = row ? Rs[lane * GLD + lane] : 1.0;
+    const double rinv = 1.0 / rii;
+    const double zk = z;
+    double d = 0.0;
+    for (int j = k - 1; j >= 0; --j) {
+      const double dj = __shfl_sync(0xffffffffu, z, j) * __shfl_sync(0xffffffffu, rinv, j);
+      if (lane == j) d = dj;
+      if (lane < j) z = fma(-Rs[lane * GLD + j], dj, z);
     }
-    double z2 = 0.0, d2 = 0.0, ndef = 0.0;
-    for (int i = lane; i < k; i += 32) {
-      const double z = Rs[i * GLD + k], d = dsh[i], rii = Rs[i * GLD + i];
-      z2 = fma(z, z, z2);
-      d2 = fma(d, d, d2);
-      if (fabs(rii) <= 1e-8) ndef += 1.0;
-      out[i] = d;
-      out[k + 4 + i] = rii;
+    double z2 = row ? zk * zk : 0.0, d2 = row ? d * d : 0.0, ndef = (row && fabs(rii) <= 1e-8) ? 1.0 : 0.0;
+    if (row) {
+      out[lane] = d;
+      out[k + 4 + lane] = rii;
     }
     z2 = warp_sum(z2);
     d2 = warp_sum(d2);
@@ -481,14 +500,14 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
   GNK_LAUNCH_CHECK(ctx);
   if (multi)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
-  cholqr_factor1_kernel<<<1, 128, 0, st>>>(parts, ctx->nranks, NB, k, sign, base + CQ_T, base + CQ_R1, status);
+  cholqr_factor1_kernel<<<1, FT, 0, st>>>(parts, ctx->nranks, NB, k, sign, base + CQ_T, base + CQ_R1, status);
   GNK_LAUNCH_CHECK(ctx);
   cholqr_gram2_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_T, status, base + CQ_PART,
                                                          ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
   GNK_LAUNCH_CHECK(ctx);
   if (multi)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
-  cholqr_factor2_kernel<<<1, 128, 0, st>>>(parts, ctx->nranks, NB, k, base + CQ_R1, status, d_out);
+  cholqr_factor2_kernel<<<1, FT, 0, st>>>(parts, ctx->nranks, NB, k, base + CQ_R1, status, d_out);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
