@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(GT, 1)
   constexpr int NBLK = nblocks(NB);
   __shared__ __align__(16) double red[NBLK * 64];
   __shared__ __align__(16) double Ts[MAXC * TLD];
-  if (*status != 0) return;  // pass 1 refused: the factor kernel reports it (uniform across the grid)
+  if (*status != 2) return;  // refused, or the refinement form was chosen (uniform across the grid)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   for (int e = threadIdx.x; e < MAXC * TLD; e += GT) Ts[e] = Tg[e];
@@ -280,10 +280,87 @@ __global__ void __launch_bounds__(GT, 1)
   reduce_gram<NBLK>(acc, red, partials, ticket, Gout);
 }
 
+// ---- pass 2, refinement form: rho = y - (sign A) d0,  g = (sign A)^T rho,  sum rho^2 ---------------------------------
+// One HBM-bound pass: a thread owns two adjacent rows (128-bit loads, a warp reads 512 contiguous bytes per column),
+// holds their k entries in registers between the two loops (rho needs the whole row before g can start), and keeps
+// its k partial sums of g in registers until the end.  FP64 work is 4 k FMAs per row pair -- the pipe idles.
+constexpr int RT = 256;  // threads per CTA
+template <int KC>
+__global__ void __launch_bounds__(RT, 1)
+    cholqr_refine_kernel(PanelSource src, double sign, const double* __restrict__ d0g, const int* __restrict__ status,
+                         int64_t rows_per_cta, double* __restrict__ partials, unsigned int* ticket,
+                         double* __restrict__ gout) {
+  __shared__ double ds[KC];
+  __shared__ double wsum[RT / 32][KC + 1];
+  if (*status != 0) return;  // the CholeskyQR2 form was chosen, or pass 1 refused (uniform across the grid)
+  const int k = src.k;
+  for (int j = threadIdx.x; j < KC; j += RT) ds[j] = (j < k) ? sign * d0g[j] : 0.0;
+  __syncthreads();
+  double g[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) g[j] = 0.0;
+  double rr = 0.0;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t limit = row0 + rows_per_cta;
+  if (limit > src.n_rows) limit = src.n_rows;
+  for (int64_t r = row0 + 2 * threadIdx.x; r < limit; r += 2 * RT) {
+    double2 a[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j)
+      a[j] = (j < k) ? __ldcs(reinterpret_cast<const double2*>(src.A + (int64_t)j * src.lda + r)) : make_double2(0.0, 0.0);
+    double2 rho = __ldcs(reinterpret_cast<const double2*>(src.y + r));
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+      rho.x = fma(-ds[j], a[j].x, rho.x);
+      rho.y = fma(-ds[j], a[j].y, rho.y);
+    }
+#pragma unroll
+    for (int j = 0; j < KC; ++j) g[j] = fma(a[j].x, rho.x, fma(a[j].y, rho.y, g[j]));
+    rr = fma(rho.x, rho.x, fma(rho.y, rho.y, rr));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < KC; ++j) {
+    const double v = warp_sum(g[j]);
+    if (lane == 0) wsum[warp][j] = v;
+  }
+  rr = warp_sum(rr);
+  if (lane == 0) wsum[warp][KC] = rr;
+  __syncthreads();
+  double* mine = partials + (int64_t)blockIdx.x * (KC + 1);
+  if (threadIdx.x <= KC) {
+    double v = wsum[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < RT / 32; ++w) v += wsum[w][threadIdx.x];
+    mine[threadIdx.x] = v;
+    __threadfence();
+  }
+  if (!grid_arrive_last(ticket)) return;
+  if (threadIdx.x <= KC) {
+    double v = 0.0;
+    const int nb = gridDim.x;
+    for (int b = 0; b < nb; ++b) v += __ldcg(partials + (int64_t)b * (KC + 1) + threadIdx.x);
+    if (threadIdx.x < k) gout[threadIdx.x] = sign * v;   // (sign A)^T rho
+    if (threadIdx.x == KC) gout[k] = v;                  // sum rho^2
+  }
+}
+
 // ---- the small factorisations (one warp) -------------------------------------------------------------------------------
 constexpr int GLD = MAXC + 1;
 constexpr double PIVOT_FLOOR_1 = 1e-12;  // pass 1: reduced pivot / diagonal entry ~ 1 / cond^2 of the leading columns
 constexpr double PIVOT_FLOOR_2 = 0.25;   // pass 2: G2 = I + O(cond^2 eps)
+// The second pass has two forms (status word written by the first factor kernel selects one, the other kernel exits):
+//   status 0  REFINE   one step of iterative refinement of the normal-equation solution: rho = y - A d0,
+//                      g = A^T rho in one HBM-bound pass (2 k FMAs per row), d = d0 + (R1^T R1)^{-1} g.  The iteration
+//                      contracts by cond^2 eps per step, so it is taken when every pivot ratio of the A columns is
+//                      >= REFINE_FLOOR (cond <~ 1e5: the correction is then <~ 1e-6 |d| and what is left after it
+//                      is below eps cond); the finishing kernel re-checks |delta| <= REFINE_ACCEPT |d| and refuses
+//                      otherwise (-> Householder).
+//   status 2  CHOLQR2  the Gram matrix of P R1^{-1} (above); any conditioning the pivot floor admits.
+//   status 1  refused by the pivot floor.
+constexpr double REFINE_FLOOR = 1e-10;
+constexpr double REFINE_ACCEPT = 1e-5;
+constexpr int GPAD = 40;  // g (k values) + sum rho^2, padded; the Gram matrix of pass 2 follows in the gather buffer
 
 // The small factorisations run in ONE CTA of 32 x 32 threads: thread (i = warp, l = lane) owns matrix entry [i][l].
 // (History: one warp with the matrix in shared memory took 40 us for c = 31 -- a chain of shared-memory round trips;
@@ -298,11 +375,12 @@ constexpr int RB = MAXC + 2;  // published row + the reciprocal of its pivot
 // Returns R[i][l] in r (zero outside the upper triangle of the leading c x c block); false (uniformly) if a pivot is
 // not safely positive.
 __device__ __forceinline__ bool block_cholesky(double a, int c, double floor_rel, double* rowbuf, double* diag,
-                                               double& r) {
+                                               double& r, double& min_ratio) {
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (i == l) diag[l] = a;  // read after the first barrier
   double a_pub = 0.0, piv_pub = 1.0;
   bool ok = true;
+  min_ratio = 1.0;  // min over the first c - 1 columns of reduced pivot / diagonal entry ~ 1 / cond^2 of [A] alone
   for (int j = 0; j < c; ++j) {
     double* rb = rowbuf + (j & 1) * RB;
     if (i == j) {
@@ -318,6 +396,7 @@ __device__ __forceinline__ bool block_cholesky(double a, int c, double floor_rel
       ok = false;
       break;
     }
+    if (j < c - 1) min_ratio = fmin(min_ratio, ajj / dj);
     if (i > j && l >= i) a = fma(-rb[i], rb[l] * rb[MAXC], a);  // the lower triangle stays zero
   }
   r = 0.0;
@@ -348,15 +427,15 @@ __device__ __forceinline__ double block_tri_inverse(const double* Rs, int c, dou
 }
 
 // the Gram matrix in fragment order (ranks added in rank order) -> my entry [i][l] (upper part; zero elsewhere)
-__device__ __forceinline__ double gather_gram(const double* __restrict__ parts, int nparts, int NB, int c) {
+__device__ __forceinline__ double gather_gram(const double* __restrict__ parts, int nparts, int NB, int c,
+                                              int stride) {
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (!(i <= l && l < c)) return 0.0;
   const int I = i >> 3, J = l >> 3;
   const int b = I * NB - I * (I - 1) / 2 + (J - I);
   const int e = b * 64 + ((i & 7) * 4 + ((l & 7) >> 1)) * 2 + (l & 1);
-  const int NE = nblocks(NB) * 64;
   double s = parts[e];
-  for (int r = 1; r < nparts; ++r) s += parts[(int64_t)r * NE + e];
+  for (int r = 1; r < nparts; ++r) s += parts[(int64_t)r * stride + e];
   return s;
 }
 
@@ -375,26 +454,37 @@ __device__ void write_refusal(int k, double* out) {
   }
 }
 
-// phase 1: R1 = chol(G), T = R1^{-1} with the sign of the A columns folded in (rows i < k of T scaled by sign).
+// phase 1: R1 = chol(G), T = R1^{-1} with the sign of the A columns folded in (rows i < k of T scaled by sign), the
+// normal-equation solution d0 = R1[:k,:k]^{-1} R1[:k,k] and ||A d0||^2 = |R1[:k,k]|^2 for the refinement form, and
+// the choice of the second pass (status).
 __global__ void __launch_bounds__(FT) cholqr_factor1_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
-                                                            double sign, double* __restrict__ Tg,
-                                                            double* __restrict__ R1g, int* __restrict__ status) {
+                                                            double sign, int method, double* __restrict__ Tg,
+                                                            double* __restrict__ R1g, double* __restrict__ d0g,
+                                                            double* __restrict__ aux, int* __restrict__ status) {
   __shared__ double Rs[MAXC * GLD];
   __shared__ double rowbuf[2 * RB];
   __shared__ double diag[MAXC];
   const int c = k + 1;
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
-  double a = gather_gram(parts, nparts, NB, c);
+  double a = gather_gram(parts, nparts, NB, c, nblocks(NB) * 64);
   if (l == k && i < k) a *= sign;  // (sign A)^T y
-  double r;
-  const bool ok = block_cholesky(a, c, PIVOT_FLOOR_1, rowbuf, diag, r);
-  if (threadIdx.x == 0) *status = ok ? 0 : 1;
+  double r, min_ratio;
+  const bool ok = block_cholesky(a, c, PIVOT_FLOOR_1, rowbuf, diag, r, min_ratio);
+  if (threadIdx.x == 0) *status = ok ? ((method != 2 && min_ratio >= REFINE_FLOOR) ? 0 : 2) : 1;
   R1g[i * MAXC + l] = ok ? r : 0.0;
   double t = 0.0;
   if (ok) {
     Rs[i * GLD + l] = r;
     __syncthreads();  // also separates the row buffers of the two loops
     t = block_tri_inverse(Rs, c, rowbuf);
+    // d0_i = sum_{m = i .. k-1} T[i][m] z[m],  z = R1[:k, k]  (warp i, lane m)
+    const double zl = (l < k) ? Rs[l * GLD + k] : 0.0;
+    const double d0 = warp_sum((l >= i && l < k) ? t * zl : 0.0);
+    if (l == 0 && i < k) d0g[i] = d0;
+    if (i == 0) {
+      const double z2 = warp_sum(zl * zl);
+      if (l == 0) aux[0] = z2;
+    }
     if (i < k) t *= sign;
   }
   Tg[i * TLD + l] = t;
@@ -404,6 +494,9 @@ __global__ void __launch_bounds__(FT) cholqr_factor1_kernel(const double* __rest
 // phase 2: R2 = chol(G2), R = R2 R1, back substitution and the scalar block of gnk_tsqr_ls.
 __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
                                                             const double* __restrict__ R1g,
+                                                            const double* __restrict__ Tg,
+                                                            const double* __restrict__ d0g,
+                                                            const double* __restrict__ aux,
                                                             const int* __restrict__ status, double* __restrict__ out) {
   __shared__ double R2s[MAXC * GLD];
   __shared__ double R1s[MAXC * GLD];
@@ -412,14 +505,65 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
   __shared__ double diag[MAXC];
   const int c = k + 1;
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (*status != 0) {
+  const int mode = *status;
+  if (mode == 1) {
     write_refusal(k, out);
     return;
   }
+  if (mode == 0) {
+    // refinement form: delta = T (T^T g), d = d0 + delta  (T carries the sign in its rows: sign^2 = 1)
+    double* gs = rowbuf;   // k + 1 values (2 * RB >= MAXC + 1)
+    double* us = diag;
+    __shared__ double dsum[2];
+    const int pstride = GPAD + nblocks(NB) * 64;
+    if (threadIdx.x <= k) {
+      double g = parts[threadIdx.x];
+      for (int r = 1; r < nparts; ++r) g += parts[(int64_t)r * pstride + threadIdx.x];
+      gs[threadIdx.x] = g;
+    }
+    R1s[i * GLD + l] = Tg[i * TLD + l];  // T
+    __syncthreads();
+    const double u = warp_sum((l <= i && i < k) ? R1s[l * GLD + i] * gs[l] : 0.0);   // u_i = sum_m T[m][i] g[m]
+    if (l == 0) us[i] = (i < k) ? u : 0.0;
+    __syncthreads();
+    const double delta = warp_sum((l >= i && l < k) ? R1s[i * GLD + l] * us[l] : 0.0);  // delta_i = sum_m T[i][m] u[m]
+    __syncthreads();
+    if (l == 0) us[i] = delta;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const bool row = l < k;
+      const double dl = row ? us[l] : 0.0;
+      const double d = row ? d0g[l] + dl : 0.0;
+      const double rii = row ? R1g[l * MAXC + l] : 1.0;
+      const double d2 = warp_sum(d * d), dl2 = warp_sum(dl * dl);
+      const double ndef = warp_sum((row && fabs(rii) <= 1e-8) ? 1.0 : 0.0);
+      if (l == 0) {
+        dsum[0] = d2;
+        dsum[1] = dl2;
+      }
+      __syncwarp();
+      if (dl2 <= REFINE_ACCEPT * REFINE_ACCEPT * d2) {  // uniform
+        if (row) {
+          out[l] = d;
+          out[k + 4 + l] = rii;
+        }
+        if (l == 0) {
+          out[k] = aux[0];
+          out[k + 1] = gs[k];
+          out[k + 2] = ndef;
+          out[k + 3] = d2;
+        }
+      }
+    }
+    __syncthreads();
+    if (!(dsum[1] <= REFINE_ACCEPT * REFINE_ACCEPT * dsum[0])) write_refusal(k, out);
+    return;
+  }
+  parts += GPAD;  // the Gram matrix of pass 2 follows g in every rank's slot
   R1s[i * GLD + l] = R1g[i * MAXC + l];
-  const double a = gather_gram(parts, nparts, NB, c);
-  double r2;
-  if (!block_cholesky(a, c, PIVOT_FLOOR_2, rowbuf, diag, r2)) {
+  const double a = gather_gram(parts, nparts, NB, c, GPAD + nblocks(NB) * 64);
+  double r2, min_ratio;
+  if (!block_cholesky(a, c, PIVOT_FLOOR_2, rowbuf, diag, r2, min_ratio)) {
     write_refusal(k, out);
     return;
   }
@@ -468,12 +612,39 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
 constexpr int64_t NE_MAX = nblocks(4) * 64;                        // 640
 constexpr int64_t CQ_PART = 0;                                     // per-CTA partials: MAX_CTAS * NE_MAX
 constexpr int64_t CQ_MAX_CTAS = 512;
-constexpr int64_t CQ_LOCAL = CQ_PART + CQ_MAX_CTAS * NE_MAX;       // this rank's Gram matrix
-constexpr int64_t CQ_ALL = CQ_LOCAL + NE_MAX;                      // all ranks' Gram matrices
-constexpr int64_t CQ_T = CQ_ALL + P2P_MAXR * NE_MAX;               // T (MAXC x TLD)
+constexpr int64_t CQ_LOCAL = CQ_PART + CQ_MAX_CTAS * NE_MAX;       // this rank's Gram matrix (pass 1)
+constexpr int64_t CQ_ALL = CQ_LOCAL + NE_MAX;                      // all ranks' Gram matrices (pass 1)
+constexpr int64_t NE2_MAX = GPAD + NE_MAX;                         // pass 2: [g, sum rho^2 | Gram matrix]
+constexpr int64_t CQ_LOCAL2 = CQ_ALL + P2P_MAXR * NE_MAX;
+constexpr int64_t CQ_ALL2 = CQ_LOCAL2 + NE2_MAX;
+constexpr int64_t CQ_T = CQ_ALL2 + P2P_MAXR * NE2_MAX;             // T (MAXC x TLD)
 constexpr int64_t CQ_R1 = CQ_T + MAXC * TLD;                       // R1 (MAXC x MAXC)
-constexpr int64_t CQ_STATUS = CQ_R1 + MAXC * MAXC;                 // int status word
+constexpr int64_t CQ_D0 = CQ_R1 + MAXC * MAXC;                     // normal-equation solution d0
+constexpr int64_t CQ_AUX = CQ_D0 + MAXC;                           // ||A d0||^2
+constexpr int64_t CQ_STATUS = CQ_AUX + 8;                          // int status word
 constexpr int64_t CQ_TOTAL = CQ_STATUS + 8;
+
+template <int KC>
+int launch_refine(gnk_ctx* ctx, const PanelSource& src, double sign, double* base, int* status, cudaStream_t st) {
+  auto kern = cholqr_refine_kernel<KC>;
+  static int occ_dev[64] = {0};
+  int& occ = occ_dev[ctx->device & 63];
+  if (occ == 0) {
+    int o = 1;
+    GNK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, RT, 0));
+    occ = o < 1 ? 1 : o;
+  }
+  constexpr int64_t GRAN = 2 * RT;
+  int64_t ctas = (int64_t)ctx->sm_count * occ;
+  if (ctas > CQ_MAX_CTAS) ctas = CQ_MAX_CTAS;
+  if (ctas * GRAN > src.n_rows) ctas = ceil_div(src.n_rows, GRAN);
+  const int64_t rows_per_cta = ceil_div(ceil_div(src.n_rows, ctas), GRAN) * GRAN;
+  ctas = ceil_div(src.n_rows, rows_per_cta);
+  kern<<<(unsigned)ctas, RT, 0, st>>>(src, sign, base + CQ_D0, status, rows_per_cta, base + CQ_PART,
+                                      ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL2);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
 
 template <int NB, int RU>
 int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k, const double* d_y, double sign,
@@ -493,21 +664,35 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
   const int NE = nblocks(NB) * 64;
   const bool multi = ctx->nranks > 1;
   GNK_REQUIRE(ctx->nranks <= P2P_MAXR, "cholqr: more ranks than the Gram gather buffer holds");
-  const double* parts = multi ? base + CQ_ALL : base + CQ_LOCAL;
+  static const int refine_on = getenv("GNK_LS_REFINE") ? atoi(getenv("GNK_LS_REFINE")) : 1;
+  const int method = (ctx->ls_method == 2 || !refine_on) ? 2 : 0;
 
+  // pass 1 and its factorisation
   cholqr_gram_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_PART,
                                                         ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
   GNK_LAUNCH_CHECK(ctx);
   if (multi)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
-  cholqr_factor1_kernel<<<1, FT, 0, st>>>(parts, ctx->nranks, NB, k, sign, base + CQ_T, base + CQ_R1, status);
+  cholqr_factor1_kernel<<<1, FT, 0, st>>>(multi ? base + CQ_ALL : base + CQ_LOCAL, ctx->nranks, NB, k, sign, method,
+                                          base + CQ_T, base + CQ_R1, base + CQ_D0, base + CQ_AUX, status);
   GNK_LAUNCH_CHECK(ctx);
+  // pass 2: the status word picks ONE of the two kernels, the other returns at once (the host does not know which:
+  // no read-back); one gather serves both
+  if (method == 0) {
+    int rc;
+    if (k <= 8) rc = launch_refine<8>(ctx, src, sign, base, status, st);
+    else if (k <= 16) rc = launch_refine<16>(ctx, src, sign, base, status, st);
+    else if (k <= 24) rc = launch_refine<24>(ctx, src, sign, base, status, st);
+    else rc = launch_refine<32>(ctx, src, sign, base, status, st);
+    if (rc) return rc;
+  }
   cholqr_gram2_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_T, status, base + CQ_PART,
-                                                         ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
+                                                         ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL2 + GPAD);
   GNK_LAUNCH_CHECK(ctx);
   if (multi)
-    if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
-  cholqr_factor2_kernel<<<1, FT, 0, st>>>(parts, ctx->nranks, NB, k, base + CQ_R1, status, d_out);
+    if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL2, base + CQ_ALL2, GPAD + NE, st)) return rc;
+  cholqr_factor2_kernel<<<1, FT, 0, st>>>(multi ? base + CQ_ALL2 : base + CQ_LOCAL2, ctx->nranks, NB, k, base + CQ_R1,
+                                          base + CQ_T, base + CQ_D0, base + CQ_AUX, status, d_out);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

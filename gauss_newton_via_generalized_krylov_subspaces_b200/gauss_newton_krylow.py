@@ -47,18 +47,22 @@ def resolve_problem(res, jac, x0, args, native_rosenbrock=False):
     return HostCallableProblem(res, jac, x0, args)
 
 
-def tsqr_solve(rt, A, lda, n_rows, k, y, sign, out, householder=False):
-    """gnk_tsqr_ls.  Large panels are factored by CholeskyQR2 (csrc/cholqr.cu), which refuses numerically rank
-    deficient panels by writing d = 0 and out[k+2] = -1 (``ls_refused``); the caller then comes back with
-    ``householder=True``, which pins the Householder TSQR for this call."""
-    prev = rt.lib.gnk_tsqr_ls_method(rt.ctx, 1) if householder else 0  # returns the previous setting (>= 0)
+def tsqr_solve(rt, A, lda, n_rows, k, y, sign, out, householder=False, method=None):
+    """gnk_tsqr_ls.  Large panels are factored on the FP64 tensor pipe (csrc/cholqr.cu: Gram matrix + Cholesky, then
+    one refinement step or the second CholeskyQR2 pass), which refuses numerically rank deficient panels by writing
+    d = 0 and out[k+2] = -1 (``ls_refused``); the caller then comes back with ``householder=True``, which pins the
+    Householder TSQR for this call.  ``method``: 0 automatic, 1 Householder, 2 CholeskyQR2 without the refinement form
+    (gnk_tsqr_ls_method)."""
+    if method is None:
+        method = 1 if householder else 0
+    prev = rt.lib.gnk_tsqr_ls_method(rt.ctx, method) if method else 0  # returns the previous setting (>= 0)
     if prev < 0:
         _lib.check(prev, "gnk_tsqr_ls_method")
     try:
         _lib.check(rt.lib.gnk_tsqr_ls(rt.ctx, ptr(A), lda, n_rows, k, ptr(y), float(sign), ptr(out), rt.stream),
                    "gnk_tsqr_ls")
     finally:
-        if householder:
+        if method:
             rt.lib.gnk_tsqr_ls_method(rt.ctx, prev)
 
 

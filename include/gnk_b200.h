@@ -133,16 +133,21 @@ int gnk_cgs_update_spmm(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* pr
  * |R_jj| <= 1e-8 (the "A is rank deficient" prints of :32-34), d_out[k+3] = ||d||^2,
  * d_out[k+4 .. 2k+4) = diag(R).  With a communicator attached the R factors of all ranks are
  * gathered and reduced identically on every rank.
- * Large panels (9 <= k+1 <= 32, >= 16384 rows, 16-byte aligned) are factored by CholeskyQR2 on the FP64 tensor pipe
- * instead (cholqr.cu: two Gram passes, R = R2 R1; same R up to row signs, same result block).  That path REFUSES
- * panels whose Gram matrix is numerically rank deficient (cond ~> 1e6, e.g. a consistent system): it then writes
+ * Large panels (9 <= k+1 <= 32, >= 16384 rows, even row count, 16-byte aligned, sign_a = +-1) are solved on the FP64
+ * tensor pipe instead (cholqr.cu): Gram matrix of the panel by DMMAs + Cholesky, then either one step of iterative
+ * refinement of the normal-equation solution (one more HBM-bound pass; chosen on the device when every Cholesky pivot
+ * ratio is >= 1e-10, i.e. cond <~ 1e5) or the second pass of CholeskyQR2 (R = R2 R1).  Same result block (diag(R) > 0;
+ * in the refinement form d_out[k] = ||A d0||^2 of the normal-equation solution d0, equal to ||A d||^2 to ~1e-7
+ * relative, and d_out[k+1] = ||y - A d0||^2).  That path REFUSES panels whose Gram matrix is numerically rank
+ * deficient (pivot ratio < 1e-12, e.g. a consistent system) or whose refinement step is not small: it then writes
  * d = 0 and d_out[k+2] = -1, and the caller re-issues the call after gnk_tsqr_ls_method(ctx, 1). */
 int gnk_tsqr_ls(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k,
                 const double* d_y, double sign_a, double* d_out, void* stream);
 
-/* Factorisation used by gnk_tsqr_ls: 0 = automatic (CholeskyQR2 where eligible, Householder TSQR otherwise; the
- * default, GNK_LS_CHOLQR=0 in the environment makes 1 the default), 1 = Householder TSQR only.  Returns the previous
- * setting, or a negative status. */
+/* Factorisation used by gnk_tsqr_ls: 0 = automatic (tensor-pipe path where eligible, Householder TSQR otherwise; the
+ * default -- GNK_LS_CHOLQR=0 in the environment disables the tensor-pipe path), 1 = Householder TSQR only,
+ * 2 = as 0 but always the second CholeskyQR2 pass, never the refinement form.  Returns the previous setting, or a
+ * negative status. */
 int gnk_tsqr_ls_method(gnk_ctx* ctx, int method);
 
 /* Fused form of gnk_stencil_apply + gnk_tsqr_ls for the Bratu stencil: the panel [sign_a * (J V_k) | r] is formed on
