@@ -230,9 +230,9 @@ def run_ours(a):
                         share_of_step=round(prof[top]["ms"] / sum(p["ms"] for p in prof.values()), 3),
                         traffic_source="dram__bytes_read+write per algorithmic byte at k=30 (profiles/r01_dram_traffic.json)"
                                        " x this run's bytes per launch",
-                        note="the projected least squares (CholeskyQR2, two reads of the panel) is bound by the FP64 "
-                             "tensor pipe for k+1 > 16 and by HBM below (DESIGN.md section 3): see `fp64`; `achieved` "
-                             "counts the panel once (algorithmic bytes); the streaming kernels are in `kernels`"
+                        note="the projected least squares reads its panel twice (Gram pass on the FP64 tensor pipe + "
+                             "refinement pass, DESIGN.md section 3), `achieved` counts the panel once (algorithmic "
+                             "bytes), `traffic` is what the two passes move; the streaming kernels are in `kernels`"
                         if top == "tsqr" else None)
         if top == "tsqr":
             # FP64 work of the projected least squares of this step (k = 1..nit): panels of 9..32 columns run
@@ -247,20 +247,23 @@ def run_ours(a):
 
             def ls_flops(kk):
                 c = kk + 1
-                if c < 9 or c > 32 or os.environ.get("GNK_LS_CHOLQR", "1") == "0":
+                if c < 3 or c > 32 or os.environ.get("GNK_LS_CHOLQR", "1") == "0":
                     return 2.0 * n_own * c * c
-                nb = 2 if c <= 16 else (3 if c <= 24 else 4)
+                nb = (c + 7) // 8
                 nblk = nb * (nb + 1) // 2
+                gram = n_own / 8.0 * 2 * nblk * 512.0                      # pass 1: 2 DMMAs per block and 8 rows
+                if os.environ.get("GNK_LS_REFINE", "1") != "0":            # refinement form: 4 k FMAs per row pair
+                    return gram + 4.0 * n_own * kk
                 tmul = sum(min(2 * j + 2, 2 * nb) for j in range(nb))
-                return n_own / 8.0 * (4 * nblk + tmul) * 512.0
+                return gram + n_own / 8.0 * (2 * nblk + tmul) * 512.0
 
             flops = sum(ls_flops(kk) for kk in range(1, nit + 1))
             tf = flops / (prof["tsqr"]["ms"] * 1e-3) / 1e12
             roofline["fp64"] = dict(achieved=round(tf, 2), peak=fpk, unit="TFLOP/s", frac=round(tf / fpk, 3),
                                     peak_source="measured DFMA throughput (DMMA shares the pipe at the same rate), "
                                                 "profiles/r01_fp64_peak.json",
-                                    flops="executed: CholeskyQR2 DMMAs x 512 for 9 <= k+1 <= 32, Householder "
-                                          "2 n (k+1)^2 for k+1 <= 8")
+                                    flops="executed: Gram DMMAs x 512 + the refinement pass (4 n k) for "
+                                          "3 <= k+1 <= 32, Householder 2 n (k+1)^2 for k = 1")
 
     # ---- end-to-end leg: host buffers in, host ndarray out ----------------------------------------
     e2e = None

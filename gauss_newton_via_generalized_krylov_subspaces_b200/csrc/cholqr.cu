@@ -704,6 +704,7 @@ int gnk_cholqr_try(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows,
                    double sign_a, double* d_out, void* stream) {
   const int c = k + 1;
   cudaStream_t st = (cudaStream_t)stream;
+  if (c <= 8) return run_cholqr<1, 4>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
   if (c <= 16) return run_cholqr<2, 2>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
   if (c <= 24) return run_cholqr<3, 1>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
   if (c <= 32) return run_cholqr<4, 1>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);

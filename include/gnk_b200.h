@@ -133,7 +133,7 @@ int gnk_cgs_update_spmm(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* pr
  * |R_jj| <= 1e-8 (the "A is rank deficient" prints of :32-34), d_out[k+3] = ||d||^2,
  * d_out[k+4 .. 2k+4) = diag(R).  With a communicator attached the R factors of all ranks are
  * gathered and reduced identically on every rank.
- * Large panels (9 <= k+1 <= 32, >= 16384 rows, even row count, 16-byte aligned, sign_a = +-1) are solved on the FP64
+ * Large panels (3 <= k+1 <= 32, >= 16384 rows, even row count, 16-byte aligned, sign_a = +-1) are solved on the FP64
  * tensor pipe instead (cholqr.cu): Gram matrix of the panel by DMMAs + Cholesky, then either one step of iterative
  * refinement of the normal-equation solution (one more HBM-bound pass; chosen on the device when every Cholesky pivot
  * ratio is >= 1e-10, i.e. cond <~ 1e5) or the second pass of CholeskyQR2 (R = R2 R1).  Same result block (diag(R) > 0;
