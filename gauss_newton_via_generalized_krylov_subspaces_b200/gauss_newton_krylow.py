@@ -35,6 +35,7 @@ _NB = _lib.GNK_MAX_BASIS
 # layout of the per-iteration scalar block (device, one D2H read per Armijo trial)
 _SC_LOSS = 2 * _NB + 8   # 2 doubles: sum(F^2) [, max|F|]
 _SC_CPREV = _SC_LOSS + 2  # sum(c_prev^2)
+_SC_FLAG = _SC_CPREV + 2   # int32 in a double slot: the deferred Krylov breakdown flag (krylow.dev_update)
 _BLK = _SC_CPREV + 6
 
 
@@ -71,6 +72,10 @@ def ls_refused(vals, k):
 
 
 class _LeastSquaresRefused(Exception):
+    pass
+
+
+class _DeferredBreakdown(Exception):
     pass
 
 
@@ -288,62 +293,79 @@ def gauss_newton_krylow(
     # GNK_FUSED_LS=1 forms J V_k inside the TSQR leaf (saves the n x k buffer and its 16nk bytes of traffic); measured
     # 14 % slower than SpMM + TSQR at 4096^2 because the leaf is issue-bound, so it is opt-in
     fuse_ls = is_bratu and os.environ.get("GNK_FUSED_LS", "0") == "1"
-    state = {}
+    state = {"pending": False}  # pending: the last basis expansion left its breakdown flag unread (see below)
+    defer_ok = (ls_solver == "qr" and not fuse_ls and not fuse_update
+                and os.environ.get("GNK_DEFER_BREAKDOWN", "1") != "0")
 
     for iter in range(1, max_iter):
-        k = krylow.k
-        # Bratu + QR: J V_k is formed inside the TSQR leaf and never stored (gnk_tsqr_ls_stencil, k <= 31)
-        fused = (fuse_ls and ls_solver == "qr" and k <= 31 and not jac_ev.transposed and jac_ev.scale == 1.0)
-        if not fused and k > jv_cap:
-            jv_cap = min(MAX_COLUMNS, max(krylow.cap, k))
-            JV = rt.empty(jv_cap * ldjv)
+        # One host synchronisation per outer iteration: the breakdown flag of the previous basis expansion is not read
+        # back when it is written (krylow.dev_update, deferred_flag) but arrives with the scalar block of this
+        # iteration's first Armijo trial.  If it was set, the speculatively appended column is retracted and the
+        # iteration is redone with the unchanged basis (breakdowns are rare: only the degenerate linear problems).
+        for attempt in (0, 1):
+            k = krylow.k
+            # Bratu + QR: J V_k is formed inside the TSQR leaf and never stored (gnk_tsqr_ls_stencil, k <= 31)
+            fused = (fuse_ls and ls_solver == "qr" and k <= 31 and not jac_ev.transposed and jac_ev.scale == 1.0)
+            if not fused and k > jv_cap:
+                jv_cap = min(MAX_COLUMNS, max(krylow.cap, k))
+                JV = rt.empty(jv_cap * ldjv)
+                jv_valid = 0
+            # projected operator and projected least squares  (:86-89)
+            if fused:
+                with rt.mark("spmm+tsqr", 8.0 * n_res_own * (k + 2)):
+                    prob.d.tsqr_fused(jac_ev.expu, krylow.V, ld, k, F_cur, -1.0, blk)
+            elif jv_valid >= k:
+                pass  # every column of J V_k was already written by the fused Gram-Schmidt update pass
+            elif jv_valid == k - 1 and k > 1:
+                with rt.mark("spmm", 8.0 * n_res_own * 3):  # only the column appended since
+                    jac_ev.matmat(krylow.col(k - 1), ld, 1, JV[(k - 1) * ldjv:], ldjv)
+            else:
+                with rt.mark("spmm", 8.0 * n_res_own * (2 * k + 1)):
+                    jac_ev.matmat(krylow.V, ld, k, JV, ldjv)
             jv_valid = 0
-        # projected operator and projected least squares  (:86-89)
-        if fused:
-            with rt.mark("spmm+tsqr", 8.0 * n_res_own * (k + 2)):
-                prob.d.tsqr_fused(jac_ev.expu, krylow.V, ld, k, F_cur, -1.0, blk)
-        elif jv_valid >= k:
-            pass  # every column of J V_k was already written by the fused Gram-Schmidt update pass
-        elif jv_valid == k - 1 and k > 1:
-            with rt.mark("spmm", 8.0 * n_res_own * 3):  # only the column appended since
-                jac_ev.matmat(krylow.col(k - 1), ld, 1, JV[(k - 1) * ldjv:], ldjv)
-        else:
-            with rt.mark("spmm", 8.0 * n_res_own * (2 * k + 1)):
-                jac_ev.matmat(krylow.V, ld, k, JV, ldjv)
-        jv_valid = 0
-        if fused:
-            pass
-        elif ls_solver == "qr":
-            with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
-                tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk)
-        elif ls_solver == "cgls":
-            cgls_dense(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, cg_rtol, blk)
-        else:
-            raise ValueError("ls_solver must be 'qr' or 'cgls'")
-        _lib.check(lib.gnk_dot(rt.ctx, k, ptr(c), ptr(c), ptr(blk, _SC_CPREV), rt.stream), "gnk_dot")
+            if fused:
+                pass
+            elif ls_solver == "qr":
+                with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
+                    tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk)
+            elif ls_solver == "cgls":
+                cgls_dense(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, cg_rtol, blk)
+            else:
+                raise ValueError("ls_solver must be 'qr' or 'cgls'")
+            _lib.check(lib.gnk_dot(rt.ctx, k, ptr(c), ptr(c), ptr(blk, _SC_CPREV), rt.stream), "gnk_dot")
 
-        # Armijo-Goldstein in coordinate space  (:91-93)
-        def trial_loss(s):
-            krylow.dev_combine(c, blk, s, x_trial)
-            with rt.mark("residual", 32.0 * n_res_own):
-                prob.residual(x_trial, F_trial, loss_slot, aux=aux[1])
-            state["vals"] = rt.read(blk, _BLK)
-            if ls_solver == "qr" and not fused and ls_refused(state["vals"], k):
-                raise _LeastSquaresRefused()
-            return float(state["vals"][_SC_LOSS])
+            # Armijo-Goldstein in coordinate space  (:91-93)
+            def trial_loss(s):
+                krylow.dev_combine(c, blk, s, x_trial)
+                with rt.mark("residual", 32.0 * n_res_own):
+                    prob.residual(x_trial, F_trial, loss_slot, aux=aux[1])
+                state["vals"] = rt.read(blk, _BLK)
+                if state["pending"] and state["vals"][_SC_FLAG:_SC_FLAG + 1].view(np.int32)[0] != 0:
+                    raise _DeferredBreakdown()
+                if ls_solver == "qr" and not fused and ls_refused(state["vals"], k):
+                    raise _LeastSquaresRefused()
+                return float(state["vals"][_SC_LOSS])
 
-        def line_search():
-            return armijo_device(trial_loss, prev_loss, lambda: float(state["vals"][k]),
-                                 lambda: float(np.sqrt(state["vals"][k + 3])))
+            def line_search():
+                return armijo_device(trial_loss, prev_loss, lambda: float(state["vals"][k]),
+                                     lambda: float(np.sqrt(state["vals"][k + 3])))
 
-        try:
-            step_length, nfev_delta = line_search()
-        except _LeastSquaresRefused:
-            # CholeskyQR2 met a numerically rank deficient panel (d = 0 was written, the trial above evaluated the
-            # unchanged iterate and is not counted): same panel again through the Householder TSQR
-            with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
-                tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk, householder=True)
-            step_length, nfev_delta = line_search()
+            try:
+                step_length, nfev_delta = line_search()
+            except _DeferredBreakdown:
+                state["pending"] = False
+                krylow.retract()
+                print(f"Generalized krylow subspace breakdown at iteration = {iter - 1}, "
+                      f"basis.shape = ({prob.p_glob}, {krylow.k})")
+                continue
+            except _LeastSquaresRefused:
+                # CholeskyQR2 met a numerically rank deficient panel (d = 0 was written, the trial above evaluated the
+                # unchanged iterate and is not counted): same panel again through the Householder TSQR
+                with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
+                    tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk, householder=True)
+                step_length, nfev_delta = line_search()
+            state["pending"] = False
+            break
         nfev += nfev_delta
         vals = state["vals"]
         if ls_solver == "qr":
@@ -374,19 +396,24 @@ def gauss_newton_krylow(
                 and not jac_ev.transposed and jac_ev.scale == 1.0):
             sp = (jac_ev, JV, ldjv, fuse_mode)
         krylow.spmm_done = False
+        # defer the breakdown read-back unless this iteration is the last one or ends with a restart (the message
+        # of :127 must appear before either)
+        defer = defer_ok and iter + 1 < max_iter and iter % krylow_restart != 0
+        dflag = ptr(blk, _SC_FLAG) if defer else None
         try:
             if version == "res_old":
-                krylow.dev_update(jac_ev, F_cur, hx, sp)
+                krylow.dev_update(jac_ev, F_cur, hx, sp, dflag)
             elif version == "res_new":
-                krylow.dev_update(jac_ev, F_trial, hx, sp)
+                krylow.dev_update(jac_ev, F_trial, hx, sp, dflag)
             elif version == "jac_old_res_old":
-                krylow.dev_update(jac_ev_old, F_cur, hx, sp)
+                krylow.dev_update(jac_ev_old, F_cur, hx, sp, dflag)
             elif version == "jac_old_res_new":
-                krylow.dev_update(jac_ev_old, F_trial, hx, sp)
+                krylow.dev_update(jac_ev_old, F_trial, hx, sp, dflag)
             else:
                 raise ValueError(
                     "Variable version must be in ['res_old','res_new','jac_old_res_old','jac_old_res_new']"
                 )
+            state["pending"] = defer
             c[krylow.k - 1:krylow.k].zero_()  # x_coordinate = np.append(x_coordinate, 0)   (:124)
         except GeneralizedKrylowSubspaceBreakdown:
             print(

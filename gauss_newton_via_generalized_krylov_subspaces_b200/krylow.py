@@ -103,12 +103,15 @@ class GeneralizedKrylowSubspace:
             _lib.check(rt.lib.gnk_combine(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(c), ptr(d), float(s),
                                           ptr(out), rt.stream), "gnk_combine")
 
-    def dev_update(self, jac_op, r, halo_exchange=None, spmm=None):
+    def dev_update(self, jac_op, r, halo_exchange=None, spmm=None, deferred_flag=None):
         """Expand the basis with -J^T r orthogonalised against V_k (krylow.py:55-73).  Raises the same
         exceptions as the reference; on Breakdown the basis is left unchanged.  ``spmm=(stencil_jacobian, JV,
         ldjv, mode)`` lets a Gram-Schmidt pass over V_k also write J V_k for the current k columns: mode "dots" fuses
         it into the first dot-product pass (gnk_stencil_apply_dots), mode "update" into the last update pass
-        (gnk_cgs_update_spmm); returns True if it did."""
+        (gnk_cgs_update_spmm); returns True if it did.
+        ``deferred_flag`` (a device pointer to an int32): the breakdown flag of krylow.py:66 is written there and NOT
+        read back; the column is appended speculatively and the caller inspects the flag with its next read-back
+        (one host synchronisation less per outer iteration) and calls ``retract()`` if it was set."""
         if self.k == self.n_glob:
             raise GeneralizedKrylowSubspaceSpansEntireSpace
         rt, lib = self.rt, self.rt.lib
@@ -155,9 +158,10 @@ class GeneralizedKrylowSubspace:
         new = self.col(self.k)
         with rt.mark("normalize", 16.0 * n):
             _lib.check(lib.gnk_normalize(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8, ptr(new),
-                                         ptr(self.flag), rt.stream), "gnk_normalize")
+                                         ptr(self.flag) if deferred_flag is None else deferred_flag, rt.stream),
+                       "gnk_normalize")
         self.spmm_done = did_spmm
-        if int(rt.read_i32(self.flag)[0]) != 0:
+        if deferred_flag is None and int(rt.read_i32(self.flag)[0]) != 0:
             raise GeneralizedKrylowSubspaceBreakdown(
                 "Normal residual is allready inside generalized Krylow Subspcae, there for gauss newton krylow "
                 "algorithm has to proceed without enlarging the subspace.")
@@ -165,6 +169,10 @@ class GeneralizedKrylowSubspace:
             halo_exchange(self.V, 2, self.k * self.ld)
         self.k += 1
         return did_spmm
+
+    def retract(self):
+        """undo a speculative append whose deferred breakdown flag turned out to be set (the column was not written)"""
+        self.k -= 1
 
     # ---- the reference's public interface (host ndarrays) -------------------------------------------
     @property

@@ -170,6 +170,50 @@ def test_host_gnk_least_squares_refusal_falls_back_to_householder(g):
     assert rel(x, np.linalg.lstsq(A, y, rcond=None)[0]) < 1e-13
 
 
+def test_host_gnk_deferred_breakdown_flag(g, capsys, monkeypatch):
+    """The Krylov breakdown flag (krylow.py:66) is read with the NEXT iteration's scalar block instead of right away
+    (one host synchronisation less per outer iteration).  compare_linear_small (grid_nodes=25, LAMBDA=0) breaks down
+    at iteration 2: the speculatively appended column must be retracted, the message printed before the next
+    callback, and the run must be identical to the one with the synchronous read (GNK_DEFER_BREAKDOWN=0)."""
+    gd = Golden("bratu_g25_linear")
+    pb = g.BratuPdeProblem(25, 5, 0)
+    res, jac = pb.make_res(gd["y"]), pb.make_jac()
+    gr = gd.run("gnk_res_old")
+    runs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GNK_DEFER_BREAKDOWN", mode)
+        events = []
+        rec = Recorder(gr["sample_idx"])
+
+        def cb(x, nfev, cg_iter):
+            events.append(("cb", nfev))
+            rec(x, nfev, cg_iter)
+
+        reads = {"n": 0}
+        rt = g.get_runtime()
+        real_read = rt.read_i32
+
+        def counting(t):
+            reads["n"] += 1
+            return real_read(t)
+
+        rt.read_i32 = counting
+        try:
+            out = g.gauss_newton_krylow(res, gd["u0"], jac, callback=cb, max_iter=100)
+            outcome = ("ok", out.nit, out.nrev, bool(out.success))
+        except g.StepLengthConvergenceError:
+            outcome = ("step",)
+        finally:
+            rt.read_i32 = real_read
+        text = capsys.readouterr().out
+        assert "Generalized krylow subspace breakdown at iteration = 2, basis.shape = (576, 2)" in text
+        runs[mode] = (outcome, [e[1] for e in events], np.array(rec.xs), reads["n"])
+        check_trace(rec, gr, 1e-10, upto=2)
+    assert runs["1"][0] == runs["0"][0] and runs["1"][1] == runs["0"][1]
+    assert np.array_equal(runs["1"][2], runs["0"][2])
+    assert runs["1"][3] < runs["0"][3]          # fewer flag read-backs in deferred mode
+
+
 def test_host_gn_and_foreign_callables(g):
     from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
     gd = Golden("rosenbrock")
