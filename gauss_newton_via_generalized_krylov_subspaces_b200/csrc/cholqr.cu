@@ -361,6 +361,7 @@ constexpr double PIVOT_FLOOR_2 = 0.25;   // pass 2: G2 = I + O(cond^2 eps)
 constexpr double REFINE_FLOOR = 1e-10;
 constexpr double REFINE_ACCEPT = 1e-5;
 constexpr int GPAD = 40;  // g (k values) + sum rho^2, padded; the Gram matrix of pass 2 follows in the gather buffer
+constexpr int64_t NE_MAX = nblocks(4) * 64;  // doubles of the widest Gram matrix in fragment order (640)
 
 // The small factorisations run in ONE CTA of 32 x 32 threads: thread (i = warp, l = lane) owns matrix entry [i][l].
 // (History: one warp with the matrix in shared memory took 40 us for c = 31 -- a chain of shared-memory round trips;
@@ -460,12 +461,25 @@ __device__ void write_refusal(int k, double* out) {
 __global__ void __launch_bounds__(FT) cholqr_factor1_kernel(const double* __restrict__ parts, int nparts, int NB, int k,
                                                             double sign, int method, double* __restrict__ Tg,
                                                             double* __restrict__ R1g, double* __restrict__ d0g,
-                                                            double* __restrict__ aux, int* __restrict__ status) {
+                                                            double* __restrict__ aux, int* __restrict__ status,
+                                                            gnk_p2p_dev pd) {
   __shared__ double Rs[MAXC * GLD];
   __shared__ double rowbuf[2 * RB];
   __shared__ double diag[MAXC];
+  __shared__ double gsh[NE_MAX];
   const int c = k + 1;
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (pd.peers) {
+    // compute step + collective in one kernel: this single CTA runs the mailbox all-reduce of the rank's Gram matrix
+    // itself (p2p_tail_allreduce, common.cuh: stores into the peers' HBM over NVLink, flags, rank-ordered sum)
+    const int NE = nblocks(NB) * 64;
+    if (threadIdx.x < NE) gsh[threadIdx.x] = parts[threadIdx.x];
+    __syncthreads();
+    p2p_tail_allreduce(pd, gsh, NE, 0);
+    __syncthreads();
+    parts = gsh;
+    nparts = 1;
+  }
   double a = gather_gram(parts, nparts, NB, c, nblocks(NB) * 64);
   if (l == k && i < k) a *= sign;  // (sign A)^T y
   double r, min_ratio;
@@ -497,7 +511,8 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
                                                             const double* __restrict__ Tg,
                                                             const double* __restrict__ d0g,
                                                             const double* __restrict__ aux,
-                                                            const int* __restrict__ status, double* __restrict__ out) {
+                                                            const int* __restrict__ status, double* __restrict__ out,
+                                                            gnk_p2p_dev pd) {
   __shared__ double R2s[MAXC * GLD];
   __shared__ double R1s[MAXC * GLD];
   __shared__ double Rs[MAXC * GLD];
@@ -505,6 +520,22 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
   __shared__ double diag[MAXC];
   const int c = k + 1;
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (pd.peers) {
+    // the mailbox all-reduce of [g, sum rho^2 | G2] comes first and unconditionally: every collective of the channel
+    // must be executed by every rank (the double-buffered slots rely on it), whatever the status word says
+    double* gsh = R2s;  // NE2_MAX <= MAXC * GLD; R2s is not written before the Cholesky below
+    const int NE2 = GPAD + nblocks(NB) * 64;
+    if (threadIdx.x < NE2) gsh[threadIdx.x] = parts[threadIdx.x];
+    __syncthreads();
+    p2p_tail_allreduce(pd, gsh, NE2, 0);
+    __syncthreads();
+    // keep the sums where the two forms expect them: a private copy, R2s is reused below
+    double* keep = Rs;  // Rs is written only after the last read of `parts`
+    if (threadIdx.x < NE2) keep[threadIdx.x] = gsh[threadIdx.x];
+    __syncthreads();
+    parts = keep;
+    nparts = 1;
+  }
   const int mode = *status;
   if (mode == 1) {
     write_refusal(k, out);
@@ -609,7 +640,6 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
 }
 
 // scratch layout inside gnk_ctx::d_cholqr (doubles)
-constexpr int64_t NE_MAX = nblocks(4) * 64;                        // 640
 constexpr int64_t CQ_PART = 0;                                     // per-CTA partials: MAX_CTAS * NE_MAX
 constexpr int64_t CQ_MAX_CTAS = 512;
 constexpr int64_t CQ_LOCAL = CQ_PART + CQ_MAX_CTAS * NE_MAX;       // this rank's Gram matrix (pass 1)
@@ -671,10 +701,15 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
   cholqr_gram_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_PART,
                                                         ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
   GNK_LAUNCH_CHECK(ctx);
-  if (multi)
+  // with the peer mailboxes attached the factor kernels (single CTAs) run the cross-rank sum themselves
+  const gnk_p2p_dev none{nullptr, 0, 1, 0ull};
+  const gnk_p2p_dev pd1 = multi ? p2p_next(ctx) : none;
+  const bool gather1 = multi && !pd1.peers;
+  if (gather1)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
-  cholqr_factor1_kernel<<<1, FT, 0, st>>>(multi ? base + CQ_ALL : base + CQ_LOCAL, ctx->nranks, NB, k, sign, method,
-                                          base + CQ_T, base + CQ_R1, base + CQ_D0, base + CQ_AUX, status);
+  cholqr_factor1_kernel<<<1, FT, 0, st>>>(gather1 ? base + CQ_ALL : base + CQ_LOCAL, gather1 ? ctx->nranks : 1, NB, k,
+                                          sign, method, base + CQ_T, base + CQ_R1, base + CQ_D0, base + CQ_AUX, status,
+                                          pd1);
   GNK_LAUNCH_CHECK(ctx);
   // pass 2: the status word picks ONE of the two kernels, the other returns at once (the host does not know which:
   // no read-back); one gather serves both
@@ -689,10 +724,12 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
   cholqr_gram2_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_T, status, base + CQ_PART,
                                                          ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL2 + GPAD);
   GNK_LAUNCH_CHECK(ctx);
-  if (multi)
+  const gnk_p2p_dev pd2 = multi ? p2p_next(ctx) : none;
+  const bool gather2 = multi && !pd2.peers;
+  if (gather2)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL2, base + CQ_ALL2, GPAD + NE, st)) return rc;
-  cholqr_factor2_kernel<<<1, FT, 0, st>>>(multi ? base + CQ_ALL2 : base + CQ_LOCAL2, ctx->nranks, NB, k, base + CQ_R1,
-                                          base + CQ_T, base + CQ_D0, base + CQ_AUX, status, d_out);
+  cholqr_factor2_kernel<<<1, FT, 0, st>>>(gather2 ? base + CQ_ALL2 : base + CQ_LOCAL2, gather2 ? ctx->nranks : 1, NB, k,
+                                          base + CQ_R1, base + CQ_T, base + CQ_D0, base + CQ_AUX, status, d_out, pd2);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -41,6 +41,21 @@ def test_library_builds_and_exports_the_header_surface():
     assert "sm_100a" in out
 
 
+def test_library_holds_the_sm100a_kernels_of_the_hot_path():
+    """the shipped .so carries the kernels bench.py and smoke() are supposed to launch: the FP64 tensor-pipe
+    instructions (DMMA) of the Gram passes, the stencil, Gram-Schmidt and least-squares kernels -- no stub library"""
+    import __graft_entry__
+    __graft_entry__.build()
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    for name in ("cholqr_gram_kernel", "cholqr_gram2_kernel", "cholqr_refine_kernel", "cholqr_factor1_kernel",
+                 "cholqr_factor2_kernel", "tsqr_quad_kernel", "apply_kernel", "residual_kernel", "combine_kernel",
+                 "dots_kernel", "update_kernel", "normalize_kernel"):
+        assert name in sass, name
+    assert sass.count("DMMA.8x8x4") > 500          # Gram passes (and the quad reductions of the Householder leaf)
+    assert "LDG.E.EF.128" in sass or "LDG.E.128" in sass
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
