@@ -27,7 +27,7 @@ from .bratu_pde_problem import BratuDeviceProblem
 from .device import DeviceVector, HostCallableProblem, get_runtime, make_layout, ptr
 from .krylow import (GeneralizedKrylowSubspace, GeneralizedKrylowSubspaceBreakdown,
                      GeneralizedKrylowSubspaceSpansEntireSpace, MAX_COLUMNS)
-from .partition import flat_layout_fields, round_up
+from .partition import flat_layout_fields, round_up, tensor_ls_on_every_rank
 from .regression_result import RegressionResult
 from .rosenbrock_problem import RosenbrockDeviceProblem
 
@@ -262,6 +262,13 @@ def gauss_newton_krylow(
     use_aux = is_bratu and prob.pb.LAMBDA != 0
     aux = [prob.new_sol() for _ in range(3)] if use_aux else [None, None, None]  # e^x: J_cur, trial, spare
     hx = prob.d.halo_exchange if (is_bratu and prob.distributed) else None
+    # Several ranks must take the SAME least-squares path (the tensor-pipe path and the Householder TSQR issue
+    # different collectives).  The library decides per call from its local slab (>= 16384 owned rows, even count), which
+    # uneven slabs can split; only the host knows every rank's slab, so it pins the Householder path for the solve
+    # unless all slabs qualify.
+    ls_method = 0
+    if is_bratu and prob.distributed and not tensor_ls_on_every_rank(prob.sol_fields["m"], rt.world):
+        ls_method = 1
 
     if native:
         prob.residual(x_trial, F_cur, loss_slot, aux=None)
@@ -327,7 +334,7 @@ def gauss_newton_krylow(
                 pass
             elif ls_solver == "qr":
                 with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
-                    tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk)
+                    tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk, method=ls_method)
             elif ls_solver == "cgls":
                 cgls_dense(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, cg_rtol, blk)
             else:

@@ -24,6 +24,16 @@ def all_counts(m: int, world: int):
     return [(b - a) * m for a, b in (slab_bounds(m, world, r) for r in range(world))]
 
 
+LS_TENSOR_MIN_ROWS = 16384  # smallest slab the tensor-pipe least squares accepts (csrc/tsqr.cu: gnk_tsqr_ls)
+
+
+def tensor_ls_on_every_rank(m: int, world: int) -> bool:
+    """True if every rank's slab qualifies for the tensor-pipe least squares (>= 16384 owned unknowns, even count).
+    The library picks its path per call from the local slab; the tensor-pipe path and the Householder TSQR issue
+    different collectives, so with slabs on both sides of the line the host must pin one path for all ranks."""
+    return all(cn >= LS_TENSOR_MIN_ROWS and cn % 2 == 0 for cn in all_counts(m, world))
+
+
 def round_up(x: int, q: int) -> int:
     return (x + q - 1) // q * q
 

@@ -42,8 +42,15 @@ def _worker(rank, world, port, G, restart, max_iter, version, out_dir):
     v = np.random.RandomState(0).normal(size=pb.n)
     gr = gd.run("gnk_res_old")
     rec = Recorder(gr["sample_idx"], err)
+    lib = g.get_runtime().lib
+    pins, real_method = [], lib.gnk_tsqr_ls_method
+    lib.gnk_tsqr_ls_method = lambda ctx, m: (pins.append(int(m)), real_method(ctx, m))[1]
     out = g.gauss_newton_krylow(res, gd["u0"], jac, callback=rec, krylow_restart=restart, max_iter=max_iter,
                                 version=version)
+    lib.gnk_tsqr_ls_method = real_method
+    # slabs of 11-17 grid rows: not every rank qualifies for the tensor-pipe least squares, so the host pins the
+    # Householder path (method 1) around every solve and releases it again -- all ranks issue the same collectives
+    assert pins and pins[0::2] == [1] * (len(pins) // 2) and pins[1::2] == [0] * (len(pins) // 2)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), y=y, Jv=J @ v, JTv=J.T @ v, xs=np.array(rec.xs),
              xnorm=np.array(rec.xnorm), nfev=np.array(rec.nfev), x=out.x, nit=out.nit, nrev=out.nrev)
     dist.barrier()

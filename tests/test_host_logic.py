@@ -93,6 +93,11 @@ def test_slab_partition():
             sizes = [b - a for a, b in bounds]
             assert max(sizes) - min(sizes) <= 1
             assert sum(P.all_counts(m, world)) == m * m
+    # the tensor-pipe least squares must be taken by all ranks or by none (different collectives)
+    assert P.tensor_ls_on_every_rank(4096, 8) and P.tensor_ls_on_every_rank(1024, 8) and P.tensor_ls_on_every_rank(128, 1)
+    assert not P.tensor_ls_on_every_rank(1001, 2)      # 501 * 1001 is odd
+    assert not P.tensor_ls_on_every_rank(181, 2)       # 91 * 181 = 16471 >= 16384 > 90 * 181
+    assert not P.tensor_ls_on_every_rank(33, 3)
     f = P.stencil_layout_fields(4096, 8, 3)
     assert (f["rows"], f["off"], f["n_own"], f["has_lo"], f["has_hi"]) == (512, 8192, 512 * 4096, 1, 1)
     assert f["ld"] % 16 == 0 and f["ld"] >= (512 + 4) * 4096
