@@ -1,26 +1,30 @@
-// cholqr.cu -- projected least squares  min || sign*A d - y ||  by CholeskyQR2 on the FP64 tensor pipe
-// (second implementation of scipy.linalg.qr + solve_triangular, gauss_newton_krylow.py:30-35, for the large
-// panels of the Bratu runs; the Householder TSQR of tsqr.cu stays the reference implementation and the fallback).
+// cholqr.cu -- projected least squares  min || sign*A d - y ||  on the FP64 tensor pipe: Gram matrix by DMMA,
+// Cholesky, then one refinement pass (or the second pass of CholeskyQR2 for ill-conditioned panels).
+// Second implementation of scipy.linalg.qr + solve_triangular (gauss_newton_krylow.py:30-35) for the large panels of
+// the Bratu runs; the Householder TSQR of tsqr.cu stays the reference implementation and the fallback.
 //
 // Why: Householder QR of a 64 x c tile is a chain of c dependent reflector steps; measured on B200 the warp-autonomous
-// leaf keeps the FP64 pipe 48 % busy (4.19 ms at n = 4096^2, c = 31).  The Gram matrix
+// leaf keeps the FP64 pipe 48 % busy (4.2 ms at n = 4096^2, c = 31).  The Gram matrix
 // G = P^T P of the panel P = [sign*A | y] has no dependency chain at all: it is a stream of independent
 // mma.sync.m8n8k4.f64 (DMMA) instructions whose A and B fragments are the SAME registers -- lane (g, t) of a warp holds
 // P[row t][column 8 I + g], which is both the A fragment of block row I and the B fragment of block column I, so
 // every panel element is loaded from HBM exactly once (128-bit loads) and used in NB + 1 DMMAs.
 //
-// Numerics: a single Cholesky factor of G loses cond(P)^2 eps.  CholeskyQR2 (Yamamoto, Nakatsukasa, Yanagisawa,
-// Fukaya 2015) repairs that with a second pass: R1 = chol(G), B = P R1^{-1} (condition number 1 + O(cond^2 eps)),
-// R2 = chol(B^T B), R = R2 R1; for cond(P) < ~1e7 the factor R is as accurate as the Householder one (normwise
-// backward error O(eps)).  B is never stored: pass 2 re-reads the panel, multiplies each 8-row group by
-// T = R1^{-1} with DMMAs whose OUTPUT fragments (lane (g, t): B^T[8 J + g][rows 2t, 2t+1]) are again directly the
-// A/B fragments of the Gram DMMAs.  The factor kernels refuse (sentinel in the result block, see gnk_b200.h) when a
-// Cholesky pivot falls below 1e-12 of its diagonal entry -- near-consistent or rank-deficient systems -- and the host
-// re-issues the solve with the Householder path.
+// Numerics: a single Cholesky factor of G loses cond(P)^2 eps.  Two second passes repair that; the first factor kernel
+// picks one ON THE DEVICE from the Cholesky pivot ratios (status word; the kernel of the other form returns at once):
+//   refinement form (cond <~ 1e5, every Bratu run): d0 from the normal equations, one HBM-bound pass
+//     rho = y - A d0, g = A^T rho, and d = d0 + (R1^T R1)^{-1} g; the iteration contracts by cond^2 eps per step;
+//   CholeskyQR2 (Yamamoto, Nakatsukasa, Yanagisawa, Fukaya 2015): B = P R1^{-1}, R2 = chol(B^T B), R = R2 R1.  B is never
+//     stored: pass 2 re-reads the panel, multiplies each 8-row group by T = R1^{-1} with DMMAs whose OUTPUT fragments
+//     (lane (g, t): B^T[8 J + g][rows 2t, 2t+1]) are again directly the A/B fragments of the Gram DMMAs.
+// The factor kernels refuse (sentinel in the result block, see gnk_b200.h) when a Cholesky pivot falls below 1e-12 of
+// its diagonal entry -- near-consistent or rank-deficient systems -- or when the refinement step is not small, and the
+// host re-issues the solve with the Householder path.
 //
-// Cost per panel row for c <= 32: 20 + 40 DMMAs per 8 rows (2.5 + 5 per row) against ~c^2 dependent DFMAs; two reads
-// of the panel (16 n c bytes).  Multi-GPU: the two c x c Gram matrices are all-gathered and summed in rank order on
-// every rank (bit-identical decisions), replacing the TSQR triangle gather and the tree levels.
+// Cost per 8 panel rows at c <= 32: 20 DMMAs (pass 1) + 4 k FMAs per row pair (refinement) or 40 DMMAs (CholeskyQR2)
+// against ~c^2 dependent DFMAs per row; two reads of the panel (16 n c bytes).  Multi-GPU: the Gram matrices are summed
+// over the ranks in rank order inside the single-CTA factor kernels (peer-mailbox all-reduce, bit-identical decisions
+// on every rank), replacing the TSQR triangle gather and the tree levels.
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -736,7 +740,8 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
 
 }  // namespace
 
-// Called by gnk_tsqr_ls (tsqr.cu) for the panels this path accepts; returns 1 when the panel is not eligible.
+// Called by gnk_tsqr_ls (tsqr.cu) for the panels it found eligible (3 <= k+1 <= 32 columns, >= 16384 rows, even row
+// count, 16-byte aligned, sign = +-1); returns 1 for a panel wider than 32 columns.
 int gnk_cholqr_try(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k, const double* d_y,
                    double sign_a, double* d_out, void* stream) {
   const int c = k + 1;
