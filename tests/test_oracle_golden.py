@@ -61,6 +61,39 @@ def test_gnk_bratu_g101(rname, kw, tol):
         assert rel(out["x"], gr["x_final"]) < tol
 
 
+@pytest.mark.parametrize("variant", ["cholqr2", "refine"])
+def test_gram_least_squares_variants_follow_the_reference_trajectory(variant):
+    """The CUDA library solves the projected least squares of the large panels with the Gram matrix + Cholesky and a
+    second pass (csrc/cholqr.cu) instead of LAPACK's Householder QR.  This is the numpy emulation of both second
+    passes inside the oracle's solver loop (the 1024^2 / 4096^2 versions are tests/ls_numerics_experiment.py): the
+    iterates must stay on the reference's golden trajectory exactly like the LAPACK-based oracle does."""
+    import scipy.linalg
+    gd, o, res, jac, err = _bratu("bratu_g101", 101)
+    steps = []
+
+    def ls(A, y, log=None):
+        k = A.shape[1]
+        if variant == "cholqr2":
+            P = np.column_stack([A, y])
+            R1 = np.linalg.cholesky(P.T @ P).T
+            B = P @ scipy.linalg.solve_triangular(R1, np.eye(k + 1))
+            R = np.linalg.cholesky(B.T @ B).T @ R1
+            return scipy.linalg.solve_triangular(R[:k, :k], R[:k, k])
+        R1 = np.linalg.cholesky(A.T @ A).T
+        solve = lambda v: scipy.linalg.solve_triangular(R1, scipy.linalg.solve_triangular(R1, v, trans="T"))
+        d0 = solve(A.T @ y)
+        delta = solve(A.T @ (y - A @ d0))
+        steps.append(np.linalg.norm(delta) / np.linalg.norm(d0))
+        return d0 + delta
+
+    gr = gd.run("gnk_res_old")
+    rec = Recorder(gr["sample_idx"], err)
+    orc.gnk(res, gd["u0"], jac, callback=rec, max_iter=45, ls=ls)
+    check_trace(rec, gr, 1e-12, upto=len(rec.xnorm))
+    if variant == "refine":   # cond(JV_k) <= 100 on this grid: the refinement step is at rounding level
+        assert max(steps) < 1e-10
+
+
 def test_gn_bratu_g101():
     gd, o, res, jac, err = _bratu("bratu_g101", 101)
     gr = gd.run("gn")
