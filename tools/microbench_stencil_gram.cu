@@ -1,0 +1,326 @@
+// microbench_stencil_gram.cu -- DRAFT for the next step of DESIGN.md section 7 (1): one kernel that applies the Bratu
+// stencil to all k basis columns of a tile (J V_k, gauss_newton_krylow.py:86), stores J V_k, AND accumulates the Gram
+// matrix of [J V_k | y] with DMMAs in the fragment layout of csrc/cholqr.cu pass 1 -- so that the least-squares panel is
+// read once instead of twice (-8 n k bytes per outer iteration, ~10 ms of the 88 ms step at 4096^2).
+//
+// STATUS (end of round 1, profiles/r01s3_microbench_stencil_gram.txt): CORRECT -- J V is bitwise identical to the
+// naive stencil and G agrees to 3e-16 at 256^2 / k = 15 and 512^2 / k = 31 -- but SLOW as laid out here: 4.72 ms at
+// 4096^2, k = 30 (1.76 TB/s over the 8.3 GB it moves) against 1.32 + 0.85 ms for apply_kernel + cholqr_gram_kernel.
+// Not profiled yet (the GPU budget ended with this run).  Suspects, in order: each warp touches 32 columns x 64 bytes
+// per step at a 32 KB stride (DRAM pages barely used; apply_kernel reads 4 KB per column and row), the 8-byte
+// left/right neighbour loads (2 per column block and step) miss L1 more often than assumed, and only one new row per
+// warp is requested per step.  Next: wider j-segments per warp (RU = 2: 16 j, 128 bytes per column), neighbours by
+// shuffle, or staging (rows x 32 columns) tiles with halo in shared memory as tsqr_stencil_kernel does.
+// It is a stand-alone program (not part of libgnk_b200.so, not built by __graft_entry__.build()):
+//
+//   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tools/microbench_stencil_gram \
+//        tools/microbench_stencil_gram.cu
+//   tools/microbench_stencil_gram 256 15        # validation against naive kernels (J V bitwise, G to 1e-12)
+//   tools/microbench_stencil_gram 4096 30       # timing: ms and GB/s over the 16 n k + 16 n bytes it moves
+//
+// Design (numbers from profiles/r01s3_cholqr_ncu.txt and DESIGN.md section 3):
+//  * a warp owns an 8-wide j-segment and marches down a strip of TR grid rows; lane (g, t) holds, for every column block
+//    I, the two grid points j = 8 seg + 2t, 2t+1 of basis column 8I+g, i.e. exactly the pass-1 fragment (the DMMA k
+//    index runs over the 4 lanes of a quad; .x and .y feed two DMMAs).  The (up, mid, down, down+1) rows of the tile
+//    live in registers (4 x NB double2), so every basis element is loaded from HBM once; the left/right neighbours are
+//    8-byte loads that hit L1 (the neighbouring lanes / warps loaded those lines);
+//  * arithmetic of J V is apply_refbits of csrc/common.cuh (scipy's order, no FMA contraction): bit-identical to
+//    apply_kernel, which the parity tests require;
+//  * FP64 pipe per 8 grid points and 32 columns: 20 DMMAs + ~80 DFMA-rate instructions = 1.5 x pass 1 today, ~0.9 ms at
+//    k = 30 -- under the 1.3 ms the 16 n k bytes take at the measured HBM peak; two rows are in flight per warp
+//    (12 warps x 2 x 2 KB = 48 KB per SM; one row gives 3.5 TB/s);
+//  * tasks (strip, segment) are numbered with the segment fastest and dealt to the warps round-robin, so that at any
+//    time the GPU sweeps a few consecutive grid rows and the CTAs' 768-byte pieces are adjacent in every column.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("%s failed: %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__);      \
+      exit(1);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+constexpr int GW = 12, GT = 32 * GW;
+constexpr int TR = 64;  // grid rows per strip
+
+struct Problem {
+  int m, rows, k;          // m x rows owned grid points (single rank: rows = m), k basis columns
+  int64_t ldv, off, ldjv;  // stored column: [2 halo rows | rows | 2 halo rows] x m, off = 2 m
+  double c_lap, c_adv, lam, sign;
+};
+
+__host__ __device__ constexpr int nblocks(int NB) { return NB * (NB + 1) / 2; }
+__host__ __device__ constexpr int blk_index(int NB, int I, int J) { return I * NB - I * (I - 1) / 2 + (J - I); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// same as csrc/common.cuh
+__device__ __forceinline__ double apply_refbits(double cu, double cl, double dg, double cd, double up, double lf,
+                                                double mid, double rt, double dn) {
+  double s = __dadd_rn(__dmul_rn(cu, up), __dmul_rn(cl, lf));
+  s = __dadd_rn(s, __dmul_rn(dg, mid));
+  s = __dadd_rn(s, __dmul_rn(cl, rt));
+  s = __dadd_rn(s, __dmul_rn(cd, dn));
+  return s;
+}
+
+// ---- naive reference kernels (validation only) ---------------------------------------------------------------------
+__global__ void ref_apply(Problem p, const double* V, const double* expu, double* JV) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = (int64_t)p.rows * p.m;
+  if (idx >= n * p.k) return;
+  const int col = (int)(idx / n);
+  const int64_t r = idx - (int64_t)col * n;
+  const int i = (int)(r / p.m), j = (int)(r - (int64_t)i * p.m);
+  const double* v = V + (int64_t)col * p.ldv + p.off;
+  const double d0 = __dadd_rn(4.0 * p.c_lap, -p.c_adv), cd = __dadd_rn(-p.c_lap, p.c_adv), cu = -p.c_lap, cl = -p.c_lap;
+  const double dg = __dadd_rn(d0, __dmul_rn(p.lam, expu[p.off + r]));
+  const double lf = j > 0 ? v[r - 1] : 0.0, rt = j + 1 < p.m ? v[r + 1] : 0.0;
+  JV[(int64_t)col * p.ldjv + r] = p.sign * apply_refbits(cu, cl, dg, cd, v[r - p.m], lf, v[r], rt, v[r + p.m]);
+}
+__global__ void ref_gram(Problem p, const double* JV, const double* y, double* G, int c) {
+  // one CTA per (a, b) entry
+  const int a = blockIdx.x / c, b = blockIdx.x % c;
+  const int64_t n = (int64_t)p.rows * p.m;
+  const double* pa = a < p.k ? JV + (int64_t)a * p.ldjv : y + p.off;
+  const double* pb = b < p.k ? JV + (int64_t)b * p.ldjv : y + p.off;
+  double s = 0.0;
+  for (int64_t r = threadIdx.x; r < n; r += blockDim.x) s = fma(pa[r], pb[r], s);
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) G[a * c + b] = sh[0];
+}
+
+// ---- the fused kernel ------------------------------------------------------------------------------------------------
+template <int NB>
+struct Row {
+  double2 v[NB];
+};
+
+template <int NB>
+__device__ __forceinline__ void load_row(Row<NB>& R, const double* const (&vb)[NB], int64_t ro) {
+#pragma unroll
+  for (int I = 0; I < NB; ++I)
+    R.v[I] = vb[I] ? __ldcs(reinterpret_cast<const double2*>(vb[I] + ro)) : make_double2(0.0, 0.0);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(GT, 1)
+    stencil_gram_kernel(Problem p, const double* __restrict__ V, const double* __restrict__ expu,
+                        const double* __restrict__ y, double* __restrict__ JV, double* __restrict__ partials) {
+  constexpr int NBLK = nblocks(NB);
+  __shared__ __align__(16) double red[NBLK * 64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m = p.m;
+  const int nseg = m / 8;  // requires m % 8 == 0 (the library would fall back to the two kernels otherwise)
+  const int nstrip = (p.rows + TR - 1) / TR;
+  const int64_t ntask = (int64_t)nseg * nstrip;
+  const int64_t gw = (int64_t)blockIdx.x * GW + warp, nw = (int64_t)gridDim.x * GW;
+  const double d0 = __dadd_rn(4.0 * p.c_lap, -p.c_adv), cd = __dadd_rn(-p.c_lap, p.c_adv), cu = -p.c_lap, cl = -p.c_lap;
+
+  double acc[NBLK][2];
+#pragma unroll
+  for (int b = 0; b < NBLK; ++b) acc[b][0] = acc[b][1] = 0.0;
+
+  for (int64_t task = gw; task < ntask; task += nw) {
+    const int strip = (int)(task / nseg), seg = (int)(task - (int64_t)strip * nseg);
+    const int j = 8 * seg + 2 * t;
+    const int i0 = strip * TR, i1 = min(i0 + TR, p.rows);
+    const bool has_l = j > 0, has_r = j + 2 < m;
+    // per column block: stencil columns read V, column k reads y (no stencil), columns beyond k are zero
+    const double* vb[NB];
+    double* ob[NB];
+    bool sten[NB];
+#pragma unroll
+    for (int I = 0; I < NB; ++I) {
+      const int col = 8 * I + g;
+      sten[I] = col < p.k;
+      vb[I] = col < p.k ? V + (int64_t)col * p.ldv + p.off + j : (col == p.k ? y + p.off + j : nullptr);
+      ob[I] = col < p.k ? JV + (int64_t)col * p.ldjv + j : nullptr;
+    }
+    const double* eb = expu + p.off + j;
+    Row<NB> up, mid, dn, dn2;
+    load_row(up, vb, (int64_t)(i0 - 1) * m);  // halo rows exist (zero at the domain boundary)
+    load_row(mid, vb, (int64_t)i0 * m);
+    load_row(dn, vb, (int64_t)(i0 + 1) * m);
+    for (int i = i0; i < i1; ++i) {
+      const int64_t ro = (int64_t)i * m;
+      load_row(dn2, vb, ro + 2 * m);  // two rows ahead; the halo has two rows, so i + 2 <= rows + 1 is always stored
+      const double2 e = __ldg(reinterpret_cast<const double2*>(eb + ro));
+      const double dga = __dadd_rn(d0, __dmul_rn(p.lam, e.x)), dgb = __dadd_rn(d0, __dmul_rn(p.lam, e.y));
+      double2 tile[NB];
+#pragma unroll
+      for (int I = 0; I < NB; ++I) {
+        if (sten[I]) {
+          const double lf = has_l ? vb[I][ro - 1] : 0.0;
+          const double rt = has_r ? vb[I][ro + 2] : 0.0;
+          const double oa = apply_refbits(cu, cl, dga, cd, up.v[I].x, lf, mid.v[I].x, mid.v[I].y, dn.v[I].x);
+          const double obv = apply_refbits(cu, cl, dgb, cd, up.v[I].y, mid.v[I].x, mid.v[I].y, rt, dn.v[I].y);
+          tile[I] = make_double2(p.sign * oa, p.sign * obv);
+          __stcs(reinterpret_cast<double2*>(ob[I] + ro), tile[I]);
+        } else {
+          tile[I] = mid.v[I];  // the y column, or zeros
+        }
+      }
+#pragma unroll
+      for (int I = 0; I < NB; ++I)
+#pragma unroll
+        for (int J = I; J < NB; ++J) {
+          const int b = blk_index(NB, I, J);
+          dmma(acc[b][0], acc[b][1], tile[I].x, tile[J].x);
+          dmma(acc[b][0], acc[b][1], tile[I].y, tile[J].y);
+        }
+      up = mid;
+      mid = dn;
+      dn = dn2;
+    }
+  }
+  // CTA sum in warp order, then one partial per CTA (fragment order, as cholqr.cu: block * 64 + lane * 2 + {0, 1})
+  for (int w = 0; w < GW; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        double2* q = reinterpret_cast<double2*>(red + b * 64 + lane * 2);
+        double2 v = make_double2(acc[b][0], acc[b][1]);
+        if (w > 0) {
+          v.x += q->x;
+          v.y += q->y;
+        }
+        *q = v;
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < NBLK * 64; e += GT) partials[(int64_t)blockIdx.x * NBLK * 64 + e] = red[e];
+}
+
+// fragment order -> dense c x c (upper part), CTA partials added in CTA order
+__global__ void gather_kernel(const double* partials, int nctas, int NB, int c, double* G) {
+  const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (!(i <= l && l < c)) return;
+  const int I = i >> 3, J = l >> 3;
+  const int b = I * NB - I * (I - 1) / 2 + (J - I);
+  const int e = b * 64 + ((i & 7) * 4 + ((l & 7) >> 1)) * 2 + (l & 1);
+  const int NE = nblocks(NB) * 64;
+  double s = 0.0;
+  for (int q = 0; q < nctas; ++q) s += partials[(int64_t)q * NE + e];
+  G[i * c + l] = s;
+  G[l * c + i] = s;
+}
+
+template <int NB>
+float run_fused(const Problem& p, const double* V, const double* expu, const double* y, double* JV, double* partials,
+                double* G, int ctas, int reps) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int r = 0; r < reps + 2; ++r) {
+    CK(cudaEventRecord(e0));
+    stencil_gram_kernel<NB><<<ctas, GT>>>(p, V, expu, y, JV, partials);
+    gather_kernel<<<1, 1024>>>(partials, ctas, NB, p.k + 1, G);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (r >= 2 && ms < best) best = ms;
+  }
+  return best;
+}
+
+int main(int argc, char** argv) {
+  const int m = argc > 1 ? atoi(argv[1]) : 256;
+  const int k = argc > 2 ? atoi(argv[2]) : 15;
+  if (m % 8 || k < 1 || k > 31) {
+    printf("usage: %s m(multiple of 8) k(1..31)\n", argv[0]);
+    return 1;
+  }
+  Problem p;
+  p.m = m;
+  p.rows = m;
+  p.k = k;
+  p.off = 2 * (int64_t)m;
+  p.ldv = ((int64_t)(m + 4) * m + 15) / 16 * 16;
+  p.ldjv = ((int64_t)m * m + 15) / 16 * 16;
+  const double h = 6.0 / (m + 1);
+  p.c_lap = 1.0 / (h * h);
+  p.c_adv = 5.0 / h;
+  p.lam = 10.0;
+  p.sign = -1.0;
+  const int c = k + 1, NB = (c + 7) / 8;
+  const int64_t n = (int64_t)m * m;
+
+  std::vector<double> hV((size_t)k * p.ldv, 0.0), hE(p.ldv, 0.0), hY(p.ldv, 0.0);
+  srand(1);
+  auto rnd = []() { return (rand() / (double)RAND_MAX - 0.5) * 2e-3; };
+  for (int col = 0; col < k; ++col)
+    for (int64_t r = 0; r < n; ++r) hV[(size_t)col * p.ldv + p.off + r] = rnd();  // halo rows stay zero (Dirichlet)
+  for (int64_t r = 0; r < n; ++r) {
+    hE[p.off + r] = exp(rnd());
+    hY[p.off + r] = rnd() * 1e3;
+  }
+  double *V, *E, *Y, *JV, *JVr, *part, *G, *Gr;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  const int ctas = prop.multiProcessorCount;
+  CK(cudaMalloc(&V, sizeof(double) * hV.size()));
+  CK(cudaMalloc(&E, sizeof(double) * hE.size()));
+  CK(cudaMalloc(&Y, sizeof(double) * hY.size()));
+  CK(cudaMalloc(&JV, sizeof(double) * (size_t)k * p.ldjv));
+  CK(cudaMalloc(&part, sizeof(double) * (size_t)ctas * 640));
+  CK(cudaMalloc(&G, sizeof(double) * 1024));
+  CK(cudaMemcpy(V, hV.data(), sizeof(double) * hV.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(E, hE.data(), sizeof(double) * hE.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(Y, hY.data(), sizeof(double) * hY.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(JV, 0, sizeof(double) * (size_t)k * p.ldjv));
+  CK(cudaMemset(G, 0, sizeof(double) * 1024));
+
+  float ms = 0;
+  if (NB == 1) ms = run_fused<1>(p, V, E, Y, JV, part, G, ctas, 5);
+  if (NB == 2) ms = run_fused<2>(p, V, E, Y, JV, part, G, ctas, 5);
+  if (NB == 3) ms = run_fused<3>(p, V, E, Y, JV, part, G, ctas, 5);
+  if (NB == 4) ms = run_fused<4>(p, V, E, Y, JV, part, G, ctas, 5);
+  const double bytes = 16.0 * n * k + 16.0 * n;  // read V, write J V, read e^u and y
+  printf("fused stencil + Gram  m=%d k=%d  %.4f ms  %.1f GB/s over %.3f GB\n", m, k, ms, bytes / ms / 1e6, bytes / 1e9);
+
+  if (m <= 1024) {  // validation against the naive kernels
+    CK(cudaMalloc(&JVr, sizeof(double) * (size_t)k * p.ldjv));
+    CK(cudaMalloc(&Gr, sizeof(double) * 1024));
+    CK(cudaMemset(JVr, 0, sizeof(double) * (size_t)k * p.ldjv));
+    ref_apply<<<(unsigned)((n * k + 255) / 256), 256>>>(p, V, E, JVr);
+    ref_gram<<<c * c, 256>>>(p, JVr, Y, Gr, c);
+    CK(cudaDeviceSynchronize());
+    std::vector<double> a((size_t)k * p.ldjv), b((size_t)k * p.ldjv), ga(1024), gb(1024);
+    CK(cudaMemcpy(a.data(), JV, sizeof(double) * a.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), JVr, sizeof(double) * b.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ga.data(), G, sizeof(double) * 1024, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(gb.data(), Gr, sizeof(double) * 1024, cudaMemcpyDeviceToHost));
+    const bool same = memcmp(a.data(), b.data(), sizeof(double) * a.size()) == 0;
+    double worst = 0.0;
+    for (int i = 0; i < c; ++i)
+      for (int l = 0; l < c; ++l) {
+        const double den = sqrt(fabs(gb[i * c + i] * gb[l * c + l])) + 1e-300;
+        worst = fmax(worst, fabs(ga[i * c + l] - gb[i * c + l]) / den);
+      }
+    printf("J V bitwise identical to the naive stencil: %s;  max |G - G_ref| / sqrt(G_ii G_ll) = %.3e (expect < 1e-12)\n",
+           same ? "yes" : "NO", worst);
+  }
+  printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+  return 0;
+}
