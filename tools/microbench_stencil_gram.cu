@@ -8,8 +8,9 @@
 // 4096^2, k = 30 (1.76 TB/s over the 8.3 GB it moves) against 1.32 + 0.85 ms for apply_kernel + cholqr_gram_kernel.
 // Not profiled yet (the GPU budget ended with this run).  Suspects, in order: each warp touches 32 columns x 64 bytes
 // per step at a 32 KB stride (DRAM pages barely used; apply_kernel reads 4 KB per column and row), the 8-byte
-// left/right neighbour loads (2 per column block and step) miss L1 more often than assumed, and only one new row per
-// warp is requested per step.  Next: wider j-segments per warp (RU = 2: 16 j, 128 bytes per column), neighbours by
+// left/right neighbour loads (2 per column block and step) miss L1 -- the tile rows are loaded with ld.global.cs
+// (evict first), so the lines the neighbours live in are probably gone when they are asked for and every one of them
+// becomes a 32-byte L2 request -- and only one new row per warp is requested per step.  Next: wider j-segments per warp (RU = 2: 16 j, 128 bytes per column), neighbours by
 // shuffle, or staging (rows x 32 columns) tiles with halo in shared memory as tsqr_stencil_kernel does.
 // It is a stand-alone program (not part of libgnk_b200.so, not built by __graft_entry__.build()):
 //
