@@ -6,12 +6,15 @@
 // STATUS (end of round 1, profiles/r01s3_microbench_stencil_gram.txt): CORRECT -- J V is bitwise identical to the
 // naive stencil and G agrees to 3e-16 at 256^2 / k = 15 and 512^2 / k = 31 -- but SLOW as laid out here: 4.72 ms at
 // 4096^2, k = 30 (1.76 TB/s over the 8.3 GB it moves) against 1.32 + 0.85 ms for apply_kernel + cholqr_gram_kernel.
-// Not profiled yet (the GPU budget ended with this run).  Suspects, in order: each warp touches 32 columns x 64 bytes
-// per step at a 32 KB stride (DRAM pages barely used; apply_kernel reads 4 KB per column and row), the 8-byte
-// left/right neighbour loads (2 per column block and step) miss L1 -- the tile rows are loaded with ld.global.cs
-// (evict first), so the lines the neighbours live in are probably gone when they are asked for and every one of them
-// becomes a 32-byte L2 request -- and only one new row per warp is requested per step.  Next: wider j-segments per warp (RU = 2: 16 j, 128 bytes per column), neighbours by
-// shuffle, or staging (rows x 32 columns) tiles with halo in shared memory as tsqr_stencil_kernel does.
+// Not profiled yet (the GPU budget ended with this run), but the sector arithmetic explains the factor: per warp and
+// step the tile loads ask for 4 x 16 = 64 sectors and the stores for 64, while the sixteen 8-byte left/right
+// neighbour loads touch ~2.5 sectors per column each = 160 sectors -- if they miss L1 (the tile rows are loaded with
+// ld.global.cs, evict first, so the lines are probably gone when the neighbours are asked for) the kernel moves
+// (64 + 160 + 64) / 128 = 2.3 x the L2 sectors it should, at a 32 KB stride (64 bytes per column and step; apply_kernel
+// reads 4 KB per column and row).  Next: neighbours by quad shuffle (only lanes t = 0 / 3 load, 64 sectors instead of
+// 160), wider segments, or -- the robust fix -- rows x 32-column tiles with a one-cell halo staged in shared memory as
+// tsqr_stencil_kernel does (5 shared loads per output: 0.6 ms of shared-memory time per solve step at k = 30, under
+// the 1.3 ms of HBM time).
 // It is a stand-alone program (not part of libgnk_b200.so, not built by __graft_entry__.build()):
 //
 //   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tools/microbench_stencil_gram \
