@@ -21,6 +21,7 @@
 //        tools/microbench_stencil_gram.cu
 //   tools/microbench_stencil_gram 256 15        # validation against naive kernels (J V bitwise, G to 1e-12)
 //   tools/microbench_stencil_gram 4096 30       # timing: ms and GB/s over the 16 n k + 16 n bytes it moves
+//   tools/microbench_stencil_gram 4096 30 2     # version 2 (neighbours by shuffle; compiled, not run yet)
 //
 // Design (numbers from profiles/r01s3_cholqr_ncu.txt and DESIGN.md section 3):
 //  * a warp owns an 8-wide j-segment and marches down a strip of TR grid rows; lane (g, t) holds, for every column block
@@ -116,14 +117,23 @@ struct Row {
   double2 v[NB];
 };
 
-template <int NB>
+// SHFL = false: version 1 (the measured one): evict-first tile loads, all neighbours by 8-byte global loads.
+// SHFL = true : version 2 (compiles, NOT run yet): default-cached tile loads, left/right neighbours from the adjacent
+//               lane of the quad by shuffle; only lanes t = 0 / t = 3 load the element of the neighbouring segment.
+template <int NB, bool SHFL>
 __device__ __forceinline__ void load_row(Row<NB>& R, const double* const (&vb)[NB], int64_t ro) {
 #pragma unroll
-  for (int I = 0; I < NB; ++I)
-    R.v[I] = vb[I] ? __ldcs(reinterpret_cast<const double2*>(vb[I] + ro)) : make_double2(0.0, 0.0);
+  for (int I = 0; I < NB; ++I) {
+    if (!vb[I])
+      R.v[I] = make_double2(0.0, 0.0);
+    else if (SHFL)
+      R.v[I] = __ldg(reinterpret_cast<const double2*>(vb[I] + ro));
+    else
+      R.v[I] = __ldcs(reinterpret_cast<const double2*>(vb[I] + ro));
+  }
 }
 
-template <int NB>
+template <int NB, bool SHFL>
 __global__ void __launch_bounds__(GT, 1)
     stencil_gram_kernel(Problem p, const double* __restrict__ V, const double* __restrict__ expu,
                         const double* __restrict__ y, double* __restrict__ JV, double* __restrict__ partials) {
@@ -160,20 +170,31 @@ __global__ void __launch_bounds__(GT, 1)
     }
     const double* eb = expu + p.off + j;
     Row<NB> up, mid, dn, dn2;
-    load_row(up, vb, (int64_t)(i0 - 1) * m);  // halo rows exist (zero at the domain boundary)
-    load_row(mid, vb, (int64_t)i0 * m);
-    load_row(dn, vb, (int64_t)(i0 + 1) * m);
+    load_row<NB, SHFL>(up, vb, (int64_t)(i0 - 1) * m);  // halo rows exist (zero at the domain boundary)
+    load_row<NB, SHFL>(mid, vb, (int64_t)i0 * m);
+    load_row<NB, SHFL>(dn, vb, (int64_t)(i0 + 1) * m);
     for (int i = i0; i < i1; ++i) {
       const int64_t ro = (int64_t)i * m;
-      load_row(dn2, vb, ro + 2 * m);  // two rows ahead; the halo has two rows, so i + 2 <= rows + 1 is always stored
+      load_row<NB, SHFL>(dn2, vb, ro + 2 * m);  // two rows ahead; the halo has two rows, so i + 2 <= rows + 1 is always stored
       const double2 e = __ldg(reinterpret_cast<const double2*>(eb + ro));
       const double dga = __dadd_rn(d0, __dmul_rn(p.lam, e.x)), dgb = __dadd_rn(d0, __dmul_rn(p.lam, e.y));
       double2 tile[NB];
 #pragma unroll
       for (int I = 0; I < NB; ++I) {
+        double lf_q = 0.0, rt_q = 0.0;
+        if (SHFL) {  // all lanes take part; lane - 1 / lane + 1 is the same column, j - 2 / j + 2, for t > 0 / t < 3
+          lf_q = __shfl_up_sync(0xffffffffu, mid.v[I].y, 1);
+          rt_q = __shfl_down_sync(0xffffffffu, mid.v[I].x, 1);
+        }
         if (sten[I]) {
-          const double lf = has_l ? vb[I][ro - 1] : 0.0;
-          const double rt = has_r ? vb[I][ro + 2] : 0.0;
+          double lf, rt;
+          if (SHFL) {
+            lf = (t > 0) ? lf_q : (has_l ? vb[I][ro - 1] : 0.0);
+            rt = (t < 3) ? rt_q : (has_r ? vb[I][ro + 2] : 0.0);
+          } else {
+            lf = has_l ? vb[I][ro - 1] : 0.0;
+            rt = has_r ? vb[I][ro + 2] : 0.0;
+          }
           const double oa = apply_refbits(cu, cl, dga, cd, up.v[I].x, lf, mid.v[I].x, mid.v[I].y, dn.v[I].x);
           const double obv = apply_refbits(cu, cl, dgb, cd, up.v[I].y, mid.v[I].x, mid.v[I].y, rt, dn.v[I].y);
           tile[I] = make_double2(p.sign * oa, p.sign * obv);
@@ -228,7 +249,7 @@ __global__ void gather_kernel(const double* partials, int nctas, int NB, int c, 
   G[l * c + i] = s;
 }
 
-template <int NB>
+template <int NB, bool SHFL>
 float run_fused(const Problem& p, const double* V, const double* expu, const double* y, double* JV, double* partials,
                 double* G, int ctas, int reps) {
   cudaEvent_t e0, e1;
@@ -237,7 +258,7 @@ float run_fused(const Problem& p, const double* V, const double* expu, const dou
   float best = 1e30f;
   for (int r = 0; r < reps + 2; ++r) {
     CK(cudaEventRecord(e0));
-    stencil_gram_kernel<NB><<<ctas, GT>>>(p, V, expu, y, JV, partials);
+    stencil_gram_kernel<NB, SHFL><<<ctas, GT>>>(p, V, expu, y, JV, partials);
     gather_kernel<<<1, 1024>>>(partials, ctas, NB, p.k + 1, G);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
@@ -295,13 +316,21 @@ int main(int argc, char** argv) {
   CK(cudaMemset(JV, 0, sizeof(double) * (size_t)k * p.ldjv));
   CK(cudaMemset(G, 0, sizeof(double) * 1024));
 
+  const int variant = argc > 3 ? atoi(argv[3]) : 1;  // 1 = version 1 (measured), 2 = version 2 (shuffle neighbours)
   float ms = 0;
-  if (NB == 1) ms = run_fused<1>(p, V, E, Y, JV, part, G, ctas, 5);
-  if (NB == 2) ms = run_fused<2>(p, V, E, Y, JV, part, G, ctas, 5);
-  if (NB == 3) ms = run_fused<3>(p, V, E, Y, JV, part, G, ctas, 5);
-  if (NB == 4) ms = run_fused<4>(p, V, E, Y, JV, part, G, ctas, 5);
+  if (variant == 2) {
+    if (NB == 1) ms = run_fused<1, true>(p, V, E, Y, JV, part, G, ctas, 5);
+    if (NB == 2) ms = run_fused<2, true>(p, V, E, Y, JV, part, G, ctas, 5);
+    if (NB == 3) ms = run_fused<3, true>(p, V, E, Y, JV, part, G, ctas, 5);
+    if (NB == 4) ms = run_fused<4, true>(p, V, E, Y, JV, part, G, ctas, 5);
+  } else {
+    if (NB == 1) ms = run_fused<1, false>(p, V, E, Y, JV, part, G, ctas, 5);
+    if (NB == 2) ms = run_fused<2, false>(p, V, E, Y, JV, part, G, ctas, 5);
+    if (NB == 3) ms = run_fused<3, false>(p, V, E, Y, JV, part, G, ctas, 5);
+    if (NB == 4) ms = run_fused<4, false>(p, V, E, Y, JV, part, G, ctas, 5);
+  }
   const double bytes = 16.0 * n * k + 16.0 * n;  // read V, write J V, read e^u and y
-  printf("fused stencil + Gram  m=%d k=%d  %.4f ms  %.1f GB/s over %.3f GB\n", m, k, ms, bytes / ms / 1e6, bytes / 1e9);
+  printf("fused stencil + Gram v%d  m=%d k=%d  %.4f ms  %.1f GB/s over %.3f GB\n", variant == 2 ? 2 : 1, m, k, ms, bytes / ms / 1e6, bytes / 1e9);
 
   if (m <= 1024) {  // validation against the naive kernels
     CK(cudaMalloc(&JVr, sizeof(double) * (size_t)k * p.ldjv));
