@@ -67,6 +67,7 @@ SIGNATURES = {
     "gnk_axpby": (_I, [_P, _L, _D, _P, _D, _P, _P, _P]),
     "gnk_dot": (_I, [_P, _L, _P, _P, _P, _P]),
     "gnk_cgls": (_I, [_P, C.POINTER(LinOp), _P, _D, _I, _P, _P, C.POINTER(_L), _P]),
+    "gnk_cgls_x0": (_I, [_P, C.POINTER(LinOp), _P, _P, _D, _I, _P, _P, C.POINTER(_L), _P]),
     "gnk_rosenbrock_residual": (_I, [_P, _L, _D, _P, _P, _P]),
     "gnk_rosenbrock_jacobian": (_I, [_P, _L, _D, _P, _P, _P, _P]),
     "gnk_comm_unique_id": (_I, [_P]),

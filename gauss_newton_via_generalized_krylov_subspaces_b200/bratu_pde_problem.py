@@ -19,8 +19,8 @@ from typing import Callable, Optional
 import numpy as np
 
 from . import _lib
-from .device import DeviceVector, get_runtime, make_layout, ptr
-from .partition import all_counts, stencil_layout_fields, stored_column_from_global
+from .device import DeviceVector, NodeSharedBuffers, get_runtime, make_layout, ptr
+from .partition import HALO, all_counts, stencil_layout_fields
 
 
 def default_u(x1, x2):
@@ -105,9 +105,7 @@ class BratuPdeProblem:
         d.upload_x(u, x)
         F = d.new_col()
         d.residual_into(x, d.zero_col(), F, None, d.scal_tmp, depth=0)
-        out = d.download_global(F)
-        np.negative(out, out=out)
-        return out
+        return np.negative(d.download_global(F))  # a private array (with several ranks the download is a shared view)
 
     def make_res(self, y):
         return BratuResidual(self, y)
@@ -135,6 +133,7 @@ class BratuDevice:
         self.scal_tmp = rt.zeros(8)
         self._zero = None
         self._host_stage = None
+        self._shared = None
 
     def new_col(self):
         return self.rt.zeros(self.ld)
@@ -159,10 +158,30 @@ class BratuDevice:
         if self.rt.world == 1:
             self.rt.upload(x_global, out[f["off"]:f["off"] + f["n_own"]])
         else:
-            stage = np.empty(self.ld)
-            stored_column_from_global(x_global, f, stage[:(f["rows"] + 2 * f["halo"]) * f["m"]])
-            stage[(f["rows"] + 2 * f["halo"]) * f["m"]:] = 0.0
-            self.rt.upload(stage, out)
+            # the rows [i0 - HALO, i1 + HALO) that lie inside the domain are ONE contiguous piece of the caller's
+            # vector: it goes to the device straight from the caller's buffer (asynchronous DMA when that is pinned),
+            # no pageable staging copy; halo rows outside the domain are the Dirichlet zeros
+            lo, hi, dst0 = self._h2d_range()
+            out[:dst0].zero_()
+            out[dst0 + (hi - lo) * f["m"]:].zero_()
+            self.rt.upload(x_global[lo * f["m"]:hi * f["m"]], out[dst0:dst0 + (hi - lo) * f["m"]])
+
+    def _h2d_range(self):
+        f = self.fields
+        lo = max(f["i0"] - HALO, 0)
+        hi = min(f["i1"] + HALO, self.pb.m)
+        return lo, hi, (lo - (f["i0"] - HALO)) * f["m"]
+
+    def h2d_doubles_per_vector(self):
+        """doubles that upload_x moves host -> device on this rank (bench.py: e2e.h2d_bytes_per_step)"""
+        if self.rt.world == 1:
+            return self.fields["n_own"]
+        lo, hi, _ = self._h2d_range()
+        return (hi - lo) * self.fields["m"]
+
+    def d2h_doubles_per_vector(self):
+        """doubles that download_global moves device -> host on this rank: its own slab"""
+        return self.fields["n_own"]
 
     def resident(self, x_global):
         """upload a global host vector once; the returned DeviceVector can be passed to the solvers as x0"""
@@ -175,11 +194,24 @@ class BratuDevice:
         rt = self.rt
         if rt.world == 1:
             return rt.download(col[f["off"]:f["off"] + f["n_own"]])
+        # Every rank copies only ITS slab device -> host, into a host buffer that all ranks of the node map
+        # (device.NodeSharedBuffers); after the closing collective each rank holds the whole vector as an ndarray over
+        # that buffer.  (Round 1 all-gathered the full vector onto every GPU and copied it N times.)
+        if self._shared is None:
+            self._shared = NodeSharedBuffers(rt, self.pb.n)
+        host, finish = self._shared.acquire()
+        start = sum(self.counts[:rt.rank])
+        host[start:start + f["n_own"]].copy_(col[f["off"]:f["off"] + f["n_own"]], non_blocking=True)
+        return finish()
+
+    def allgather_device(self, col):
+        """the global vector on EVERY rank's GPU (owned parts all-gathered over NVLink) -- for device-side consumers"""
+        rt = self.rt
         full = rt.empty(self.pb.n)
         counts = (C.c_int64 * rt.world)(*self.counts)
         _lib.check(rt.lib.gnk_comm_allgather_owned(rt.ctx, C.byref(self.lay), ptr(col), ptr(full), counts, rt.stream),
                    "gnk_comm_allgather_owned")
-        return rt.download(full)
+        return full
 
     def residual_into(self, x, y, F, expu, loss_slot, depth=1):
         rt = self.rt

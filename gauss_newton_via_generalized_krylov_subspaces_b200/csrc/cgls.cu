@@ -119,9 +119,10 @@ struct Cg {
 
 }  // namespace
 
-extern "C" int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, double rtol, int preconditioner,
-                        double* d_x, double* d_work, int64_t* iters, void* stream) {
+extern "C" int gnk_cgls_x0(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, const double* d_x0, double rtol,
+                           int preconditioner, double* d_x, double* d_work, int64_t* iters, void* stream) {
   GNK_REQUIRE(ctx && op && d_y && d_x && d_work && iters, "gnk_cgls: null argument");
+  GNK_REQUIRE(d_x0 != d_x, "gnk_cgls: x0 and x must not alias (x0 is read again by the second run)");
   GNK_REQUIRE(op->kind == 0 || op->kind == 1, "gnk_cgls: unknown operator kind");
   Cg cg;
   cg.ctx = ctx;
@@ -165,7 +166,7 @@ extern "C" int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, do
   if (int rc = cg.read(S_BB, 1, &bb)) return rc;
   *iters = 0;
   const double bn = sqrt(bb);
-  if (bn == 0.0) {
+  if (bn == 0.0) {  // scipy returns the zero vector b itself (postprocess(b)), whatever x0 was
     GNK_CUDA(cudaMemcpyAsync(d_x + o, b + o, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     return 0;
   }
@@ -187,8 +188,16 @@ extern "C" int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, do
       reciprocal_kernel<<<cg.grid, TPB, 0, st>>>(n, dinv + o, dinv + o);
       GNK_LAUNCH_CHECK(ctx);
     }
-    GNK_CUDA(cudaMemsetAsync(d_x + o, 0, sizeof(double) * n, st));
-    GNK_CUDA(cudaMemcpyAsync(r + o, b + o, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (d_x0) {
+      // scipy's cg with an initial guess: x = x0, r = b - A^T A x0; the tolerance stays relative to |b|
+      GNK_CUDA(cudaMemcpyAsync(d_x + o, d_x0 + o, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+      if (int rc = cg.apply(d_x, t, 0)) return rc;
+      if (int rc = cg.apply(t, q, 1)) return rc;
+      if (int rc = gnk_axpby(ctx, n, 1.0, b + o, -1.0, q + o, r + o, st)) return rc;
+    } else {
+      GNK_CUDA(cudaMemsetAsync(d_x + o, 0, sizeof(double) * n, st));
+      GNK_CUDA(cudaMemcpyAsync(r + o, b + o, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    }
     for (int64_t it = 0; it < maxiter; ++it) {
       cg_precond_kernel<<<cg.grid, TPB, 0, st>>>(n, r + o, use_m ? dinv + o : nullptr, z + o, part,
                                                  ctx->d_tickets + TK_CG, cg.scal);
@@ -210,4 +219,9 @@ extern "C" int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, do
   }
   GNK_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+extern "C" int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, double rtol, int preconditioner,
+                        double* d_x, double* d_work, int64_t* iters, void* stream) {
+  return gnk_cgls_x0(ctx, op, d_y, nullptr, rtol, preconditioner, d_x, d_work, iters, stream);
 }

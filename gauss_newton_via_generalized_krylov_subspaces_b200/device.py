@@ -3,9 +3,12 @@ torch.distributed plumbing, every arithmetic step in libgnk_b200.so (no CPU fall
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
+import mmap
 import os
-import sys
+import time
+import weakref
 
 import numpy as np
 
@@ -143,6 +146,13 @@ class Runtime:
         self.sync()
         return h.numpy()
 
+    def host_register(self, addr, nbytes):
+        """page-lock host memory this process did not allocate through torch (a /dev/shm mapping), so that copies to
+        and from it are asynchronous DMA"""
+        rc = self.torch.cuda.cudart().cudaHostRegister(int(addr), int(nbytes), 0)
+        if int(rc) != 0:
+            raise _lib.GnkError(f"cudaHostRegister failed (cudaError {int(rc)})")
+
     def launches(self):
         return int(self.lib.gnk_launch_count(self.ctx))
 
@@ -169,6 +179,93 @@ class _Mark:
             e1.record()
             self.rt.prof.setdefault(self.name, []).append((self.e0, e1, self.nbytes))
         return False
+
+
+class NodeSharedBuffers:
+    """Host result buffers shared by the ranks of ONE node (files in /dev/shm mapped by every rank, page-locked with
+    cudaHostRegister): a rank copies only ITS slab device -> host, and every rank still sees the whole vector -- the
+    N-fold all-gather + N full-vector D2H copies of round 1 become one slab copy per rank.
+
+    All ranks call ``acquire()`` together.  A buffer is handed out again only when NO rank holds an array over it any
+    more: every rank tests its own weak reference, the flags are max-reduced over the ranks (one tiny collective), so
+    all ranks pick the same buffer or grow the pool together."""
+
+    def __init__(self, rt, n_doubles):
+        self.rt, self.n = rt, int(n_doubles)
+        box = [f"gnk_b200_{os.getpid()}_{time.monotonic_ns()}"]
+        rt.torch.distributed.broadcast_object_list(box, src=0)
+        self.token = box[0]
+        self.bufs = []      # [mmap, host tensor over it, weakref to the ctypes owner of the array handed out | None]
+        self.flags = rt.zeros(16)
+        atexit.register(self.close)
+
+    def _path(self, i):
+        return f"/dev/shm/{self.token}_{i}"
+
+    def _grow(self):
+        rt, i = self.rt, len(self.bufs)
+        if i >= 16:
+            raise _lib.GnkError("more than 16 full-vector results are alive at once; copy or drop some")
+        nbytes = 8 * self.n
+        if rt.rank == 0:
+            with open(self._path(i), "wb") as f:
+                f.truncate(nbytes)
+        rt.torch.distributed.barrier()
+        fd = os.open(self._path(i), os.O_RDWR)
+        try:
+            mm = mmap.mmap(fd, nbytes)
+        finally:
+            os.close(fd)
+        host = rt.torch.frombuffer(mm, dtype=rt.torch.float64, count=self.n)
+        rt.host_register(host.data_ptr(), nbytes)
+        self.bufs.append([mm, host, None])
+        return i
+
+    def acquire(self):
+        """-> (host tensor over the whole buffer, finish) ; ``finish()`` (collective, after this rank's copy has been
+        enqueued) waits until every rank's part is in host memory and returns the ndarray to hand out"""
+        rt = self.rt
+        nb = len(self.bufs)
+        pick = None
+        if nb:
+            busy = [1.0 if (b[2] is not None and b[2]() is not None) else 0.0 for b in self.bufs]
+            stage = rt.pinned(16)
+            stage.zero_()
+            stage[:nb] = rt.torch.tensor(busy, dtype=rt.torch.float64)
+            self.flags.copy_(stage, non_blocking=True)
+            rt.allreduce(self.flags, nb, 1)
+            vals = rt.read(self.flags, nb)
+            free = np.nonzero(vals == 0.0)[0]
+            if free.size:
+                pick = int(free[0])
+        if pick is None:
+            pick = self._grow()
+        mm, host, _ = self.bufs[pick]
+
+        def finish():
+            rt.sync()                      # this rank's slab is in host memory
+            rt.allreduce(self.flags, 1, 1)   # ... and so is everybody else's (any collective is a barrier)
+            rt.read(self.flags, 1)
+            owner = (C.c_double * self.n).from_buffer(mm)
+            self.bufs[pick][2] = weakref.ref(owner)
+            out = np.frombuffer(owner, dtype=np.float64)
+            out.flags.writeable = False  # the memory is shared by all ranks: in-place edits would hit every rank
+            return out
+
+        return host, finish
+
+    def close(self):
+        for i, (mm, host, _) in enumerate(self.bufs):
+            try:
+                self.rt.torch.cuda.cudart().cudaHostUnregister(host.data_ptr())
+            except Exception:
+                pass
+            if self.rt.rank == 0:
+                try:
+                    os.unlink(self._path(i))
+                except OSError:
+                    pass
+        self.bufs = []
 
 
 def ptr(t, offset=0):
@@ -215,13 +312,19 @@ class DeviceVector:
             self._t = None
         return self._host
 
-    def detach_if_shared(self):
-        """called by the solver after a callback returned: if the callback kept a reference, take the
-        host snapshot now, because the device buffer is about to be overwritten."""
-        if self._host is None and sys.getrefcount(self) > 3:
+    def release_or_snapshot(self):
+        """Ownership hand-off after a callback returned.  The solver calls this as ``ref = weakref.ref(xv); del xv;
+        DeviceVector.settle(ref)``: if the weak reference is dead nobody kept the vector and nothing happens; if it is
+        alive the callback (or a wrapper, a debugger, a list ...) holds it, and the host snapshot is taken NOW, because
+        the device buffer is about to be overwritten.  No reference counts are inspected."""
+        if self._host is None:
             self.materialize()
-        elif self._host is None:
-            self._t = None
+
+    @staticmethod
+    def settle(ref):
+        v = ref()
+        if v is not None:
+            v.release_or_snapshot()
 
     def __array__(self, dtype=None, copy=None):
         a = self.materialize()

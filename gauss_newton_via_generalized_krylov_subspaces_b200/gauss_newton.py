@@ -11,6 +11,7 @@ reference does (:118-120).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Callable, Tuple
 
 import numpy as np
@@ -19,18 +20,18 @@ from . import _lib
 from .armijo_goldstein import armijo_device, armijo_goldstein
 from .bratu_pde_problem import BratuDeviceProblem, StencilJacobian
 from .device import CsrJacobian, DeviceVector, get_runtime, make_layout, ptr
-from .gauss_newton_krylow import resolve_problem, tsqr_solve
+from .gauss_newton_krylow import _report_rank, require_single_rank_unless_sharded, resolve_problem, tsqr_solve
 from .partition import flat_layout_fields, round_up
 from .regression_result import RegressionResult
 
 _NB = _lib.GNK_MAX_BASIS
 
 
-def _cgls(rt, linop, y, rtol, preconditioner, x_out, vlen):
+def _cgls(rt, linop, y, rtol, preconditioner, x_out, vlen, x0=None):
     work = rt.zeros(7 * vlen)
     iters = C.c_int64(0)
-    _lib.check(rt.lib.gnk_cgls(rt.ctx, C.byref(linop), ptr(y), float(rtol), int(bool(preconditioner)), ptr(x_out),
-                               ptr(work), C.byref(iters), rt.stream), "gnk_cgls")
+    _lib.check(rt.lib.gnk_cgls_x0(rt.ctx, C.byref(linop), ptr(y), ptr(x0), float(rtol), int(bool(preconditioner)),
+                                  ptr(x_out), ptr(work), C.byref(iters), rt.stream), "gnk_cgls")
     return int(iters.value)
 
 
@@ -39,16 +40,19 @@ def cg_least_squares(A, y, x0=None, cg_rtol=1e-4, preconditioner=True):
 
     A: scipy sparse matrix / ndarray / device stencil operator, y: ndarray.  Returns (x, cg_iter) where cg_iter
     sums the unpreconditioned and the preconditioned run when ``preconditioner`` is False (reference quirk)."""
-    if x0 is not None:
-        raise NotImplementedError("cg_least_squares: only x0=None (the reference's only use) is supported")
     rt = get_runtime()
     if isinstance(A, StencilJacobian):
         d = A.pb.dev
         ycol = d.new_col()
         d.upload_x(y, ycol)
         x = d.new_col()
-        it = _cgls(rt, A.linop(1.0), ycol, cg_rtol, preconditioner, x, d.ld)
+        x0col = None
+        if x0 is not None:  # the initial guess scipy's cg is given (:46,:56); both runs start from it
+            x0col = d.new_col()
+            d.upload_x(x0, x0col)
+        it = _cgls(rt, A.linop(1.0), ycol, cg_rtol, preconditioner, x, d.ld, x0col)
         return d.download_global(x), it
+    require_single_rank_unless_sharded(rt, None, "cg_least_squares")
     import scipy.sparse as sp
     op = A if isinstance(A, CsrJacobian) else CsrJacobian(rt, A, isinstance(A, (sp.sparray, sp.spmatrix)))
     y = np.asarray(y, dtype=np.float64).reshape(-1)
@@ -56,7 +60,11 @@ def cg_least_squares(A, y, x0=None, cg_rtol=1e-4, preconditioner=True):
     dy = rt.zeros(vlen)
     rt.upload(y, dy[:op.n_res])
     x = rt.zeros(vlen)
-    it = _cgls(rt, op.linop(1.0), dy, cg_rtol, preconditioner, x, vlen)
+    dx0 = None
+    if x0 is not None:
+        dx0 = rt.zeros(vlen)
+        rt.upload(np.asarray(x0, dtype=np.float64).reshape(-1), dx0[:op.p])
+    it = _cgls(rt, op.linop(1.0), dy, cg_rtol, preconditioner, x, vlen, dx0)
     return rt.download(x[:op.p]), it
 
 
@@ -85,6 +93,7 @@ def gauss_newton(
     is_bratu = isinstance(prob, BratuDeviceProblem)
     if is_bratu and prob.distributed:
         raise NotImplementedError("gauss_newton: the full-space solver runs on one GPU (replicas only)")
+    require_single_rank_unless_sharded(rt, prob, "gauss_newton")
     success = False
     cg_iter = None
     sol = prob.sol_fields
@@ -201,8 +210,9 @@ def gauss_newton(
 
         xv = DeviceVector(prob, x, prob.p_glob)
         callback(x=xv, nfev=nfev, cg_iter=cg_iter)
-        xv.detach_if_shared()
+        xref = weakref.ref(xv)
         del xv
+        DeviceVector.settle(xref)  # a callback that kept x gets its host snapshot before the buffer is reused
 
         if step_length**2 * squared_sum_d <= tol**2 * squared_sum_x_prev:
             success = True

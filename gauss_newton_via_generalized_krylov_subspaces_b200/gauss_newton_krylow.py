@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Any, Callable, Optional, Tuple
 
 import numpy as np
@@ -46,6 +47,19 @@ def resolve_problem(res, jac, x0, args, native_rosenbrock=False):
             and os.environ.get("GNK_NATIVE_ROSENBROCK", "1") != "0":
         return RosenbrockDeviceProblem(x0)
     return HostCallableProblem(res, jac, x0, args)
+
+
+def require_single_rank_unless_sharded(rt, prob, who):
+    """Only the Bratu problem is row-sharded over the ranks of a process group.  Every other problem (foreign
+    callables, the chained Rosenbrock problem, stand-alone least squares) holds FULL vectors on every rank, while the
+    library's reductions sum over all ranks once a communicator is attached -- norms would come out sqrt(world) too
+    large and the Armijo test would compare against world * g.  SURVEY 8e asks for "replicas only" there: run those
+    problems in processes without a process group (or with world_size 1)."""
+    if rt.world > 1 and not getattr(prob, "distributed", False):
+        raise _lib.GnkError(
+            f"{who}: this problem is not row-sharded (only BratuPdeProblem is), but the process group has "
+            f"{rt.world} ranks and the library would sum its reductions over all of them.  Run replicated problems "
+            "in single-rank processes (no torch.distributed process group).")
 
 
 def tsqr_solve(rt, A, lda, n_rows, k, y, sign, out, householder=False, method=None):
@@ -159,6 +173,7 @@ def linear_least_squares(A, y):
     """Least squares solution of ||y - A x|| by Householder TSQR on the device (reference :16-36: economic QR,
     a print per |r_kk| <= 1e-8, triangular solve).  A: (n, k) ndarray, y: (n,) ndarray -> x: (k,) ndarray."""
     rt = get_runtime()
+    require_single_rank_unless_sharded(rt, None, "linear_least_squares")
     A = np.asarray(A, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
     n, k = A.shape
@@ -220,9 +235,13 @@ def gauss_newton_krylow(
     rt = get_runtime()
     lib = rt.lib
     success = False
-    x0_resident = isinstance(x0, DeviceVector) and x0._t is not None  # a start vector already in HBM
+    # a start vector already in HBM is used in place only by the problem that made it (BratuPdeProblem.dev.resident);
+    # for every other problem a DeviceVector is an ordinary array-like and is read through its host copy
+    x0_resident = (isinstance(x0, DeviceVector) and x0._t is not None and BratuDeviceProblem.match(res, jac)
+                   and not args and getattr(x0._owner, "pb", None) is res.pb)
     x0_host = None if x0_resident else np.asarray(x0, dtype=np.float64).reshape(-1)
     prob = resolve_problem(res, jac, x0 if x0_resident else x0_host, args, native_rosenbrock=True)
+    require_single_rank_unless_sharded(rt, prob, "gauss_newton_krylow")
     if krylow_restart is None:
         krylow_restart = max_iter
 
@@ -311,6 +330,7 @@ def gauss_newton_krylow(
         # iteration is redone with the unchanged basis (breakdowns are rare: only the degenerate linear problems).
         for attempt in (0, 1):
             k = krylow.k
+            state["rank_reported"] = False
             # Bratu + QR: J V_k is formed inside the TSQR leaf and never stored (gnk_tsqr_ls_stencil, k <= 31)
             fused = (fuse_ls and ls_solver == "qr" and k <= 31 and not jac_ev.transposed and jac_ev.scale == 1.0)
             if not fused and k > jv_cap:
@@ -351,6 +371,11 @@ def gauss_newton_krylow(
                     raise _DeferredBreakdown()
                 if ls_solver == "qr" and not fused and ls_refused(state["vals"], k):
                     raise _LeastSquaresRefused()
+                if ls_solver == "qr" and not state["rank_reported"]:
+                    # the reference prints / raises inside linear_least_squares (:32-35), i.e. before any trial is
+                    # judged: an exactly singular R must surface as LinAlgError, not as 100 rejected NaN trials
+                    state["rank_reported"] = True
+                    _report_rank(state["vals"], k)
                 return float(state["vals"][_SC_LOSS])
 
             def line_search():
@@ -370,13 +395,12 @@ def gauss_newton_krylow(
                 # unchanged iterate and is not counted): same panel again through the Householder TSQR
                 with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
                     tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk, householder=True)
+                state["rank_reported"] = False
                 step_length, nfev_delta = line_search()
             state["pending"] = False
             break
         nfev += nfev_delta
         vals = state["vals"]
-        if ls_solver == "qr":
-            _report_rank(vals, k)
         squared_sum_d = float(vals[k + 3])
         squared_sum_x_prev = float(vals[_SC_CPREV])
 
@@ -385,8 +409,9 @@ def gauss_newton_krylow(
 
         xv = DeviceVector(prob, x_trial, prob.p_glob)
         callback(x=xv, nfev=nfev, cg_iter=None)
-        xv.detach_if_shared()
-        del xv
+        xref = weakref.ref(xv)
+        del xv                      # if the callback kept x, the weak reference is still alive ...
+        DeviceVector.settle(xref)   # ... and x takes its host snapshot before the buffer is reused
 
         if step_length**2 * squared_sum_d <= tol**2 * squared_sum_x_prev:
             success = True

@@ -198,6 +198,11 @@ typedef struct {
  * 7 stored columns (stencil) / 7 * roundup16(max(p, n_res)) doubles (CSR).  Synchronises the stream. */
 int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, double rtol, int preconditioner,
              double* d_x, double* d_work, int64_t* iters, void* stream);
+/* The same with the initial guess that cg_least_squares forwards to scipy's cg (gauss_newton.py:14,46,56: `x0=x0`):
+ * both runs start from d_x0 (same layout as d_x, must not alias it; NULL = zero start = gnk_cgls) with
+ * r = A^T y - A^T A x0, while the stopping threshold stays rtol * ||A^T y||. */
+int gnk_cgls_x0(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, const double* d_x0, double rtol,
+                int preconditioner, double* d_x, double* d_work, int64_t* iters, void* stream);
 
 /* ---- chained Rosenbrock problem on the device (rosenbrock_problem.py:8-19) -------------- */
 /* F = sqrt2 * [10 (x[1:] - x[:-1]^2) ; 1 - x[:-1]]  (2p-2 values), numpy's rounding order (res, :8-12). */

@@ -6,6 +6,7 @@ which does not exist on the GPU box); the fixtures it writes are committed.
     python oracle/gen_golden.py small          # all n <= 1e4 configs (~1 min)
     python oracle/gen_golden.py g1025          # Bratu 1024^2 (~5 min)
     python oracle/gen_golden.py g4097          # Bratu 4096^2, 30 iterations (~10 min, 25 GB)
+    python oracle/gen_golden.py ttt            # converging grid_resolution=1 runs at 256^2..1024^2 (~4 min)
 
 Per solver run a fixture stores: the RegressionResult fields, and per callback
 |x|_2, error(x), loss 0.5|res(x)|^2, nfev, cg_iter and x sampled at fixed indices
@@ -233,6 +234,17 @@ def g4097():
     ), y_sample=y[sample_idx(y.shape[0])], u0_sample=u0[sample_idx(u0.shape[0])])
 
 
+def ttt():
+    """time-to-tolerance configurations beyond compare_without_scaling (bratu_pde_test.py:76-103, grid_resolution=1):
+    the same set-up on larger grids with version="res_new", which genuinely converges (tol=1e-8) within 100 iterations
+    (res_old needs 106 at grid_nodes=257: more columns than max_iter=100 allows)."""
+    for G in (257, 513, 1025):
+        pb, y, res, jac, err, u0 = bratu_setup(G, 5, 10, h=1)
+        save(f"bratu_g{G}_h1", dict(
+            gnk_res_new=run(gauss_newton_krylow, res, u0, jac, err, loss_every=0, max_iter=100, version="res_new"),
+        ), y_sample=y[sample_idx(y.shape[0])], u0_sample=u0[sample_idx(u0.shape[0])])
+
+
 def sensitivity(G, name, runs_kw):
     """The reference against ITSELF when the start vector u0 is perturbed by one unit in the last place (relative
     2^-52, random signs, seed 7).  The deviation of the perturbed trace from the unperturbed one is the conditioning of
@@ -265,4 +277,4 @@ def sens4097():
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["small"]:
         dict(small=small, g1025=g1025, g4097=g4097, kernels=kernels_fixture, sens101=sens101, sens1025=sens1025,
-             sens4097=sens4097)[what]()
+             sens4097=sens4097, ttt=ttt)[what]()

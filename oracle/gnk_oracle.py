@@ -266,8 +266,9 @@ def ls_qr(A, y, log=None):
     return scipy.linalg.solve_triangular(r, q.T @ y)
 
 
-def pcg(matvec, b, minv=None, rtol=1e-5, maxiter=None):
-    """scipy 1.18.1 sparse.linalg.cg restated (x0 = 0).  Returns (x, n_callbacks)."""
+def pcg(matvec, b, minv=None, rtol=1e-5, maxiter=None, x0=None):
+    """scipy 1.18.1 sparse.linalg.cg restated (x0 = 0 unless given: then x = x0.copy(), r = b - A x0, and the
+    tolerance stays relative to |b|).  Returns (x, n_callbacks)."""
     bn = np.linalg.norm(b)
     atol = max(0.0, rtol * bn)
     if bn == 0:
@@ -275,8 +276,12 @@ def pcg(matvec, b, minv=None, rtol=1e-5, maxiter=None):
     n = b.shape[0]
     if maxiter is None:
         maxiter = 10 * n
-    x = np.zeros_like(b)
-    r = b.copy()
+    if x0 is None:
+        x = np.zeros_like(b)
+        r = b.copy()
+    else:
+        x = np.array(x0, dtype=np.float64)
+        r = b - matvec(x)
     rho_prev = None
     p = None
     its = 0
@@ -299,16 +304,17 @@ def pcg(matvec, b, minv=None, rtol=1e-5, maxiter=None):
     return x, its
 
 
-def cgls(A, y, rtol=1e-4, preconditioner=True):
+def cgls(A, y, rtol=1e-4, preconditioner=True, x0=None):
     """cg_least_squares, gauss_newton.py:11-60, including its quirk: with
     preconditioner=False an unpreconditioned CG runs first, is discarded, and
-    the Jacobi-preconditioned CG always runs; cg_iter is the sum."""
+    the Jacobi-preconditioned CG always runs; cg_iter is the sum.  ``x0`` is
+    the initial guess both runs are given (:46,:56)."""
     AT = A.T
     mv = lambda v: AT @ (A @ v)
     b = AT @ y
     total = 0
     if not preconditioner:
-        _, its = pcg(mv, b, None, rtol)
+        _, its = pcg(mv, b, None, rtol, x0=x0)
         total += its
     if sp.issparse(A):
         diag = np.asarray(A.multiply(A).sum(axis=0)).reshape(-1)
@@ -316,7 +322,7 @@ def cgls(A, y, rtol=1e-4, preconditioner=True):
         diag = np.sum(A * A, axis=0)
     else:
         diag = A.normal_diagonal()
-    x, its = pcg(mv, b, 1.0 / diag, rtol)
+    x, its = pcg(mv, b, 1.0 / diag, rtol, x0=x0)
     return x, total + its
 
 

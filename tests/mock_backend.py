@@ -296,6 +296,9 @@ class MockLib:
 
     # ---- CGLS (scipy cg restated; single rank) ----
     def gnk_cgls(self, ctx, op, y, rtol, preconditioner, x, work, iters, stream):
+        return self.gnk_cgls_x0(ctx, op, y, None, rtol, preconditioner, x, work, iters, stream)
+
+    def gnk_cgls_x0(self, ctx, op, y, x0, rtol, preconditioner, x, work, iters, stream):
         op = obj(op)
         it_out = obj(iters)
         if op.kind == 0:
@@ -328,10 +331,11 @@ class MockLib:
         b = apply(yv, 1)
         mv = lambda v: apply(apply(v, 0), 1)  # noqa: E731
         total = 0
+        start = None if isnull(x0) else (arr(x0, ld)[off:off + n].copy() if op.kind == 0 else arr(x0, op.p).copy())
         if not preconditioner:
-            _, its = pcg(mv, b, None, rtol)
+            _, its = pcg(mv, b, None, rtol, x0=start)
             total += its
-        sol, its = pcg(mv, b, minv, rtol)
+        sol, its = pcg(mv, b, minv, rtol, x0=start)
         xv[:] = sol
         it_out.value = total + its
         return 0
@@ -437,6 +441,9 @@ class MockRuntime(device.Runtime):
 
     def download(self, t):
         return t.detach().clone().numpy()
+
+    def host_register(self, addr, nbytes):
+        pass
 
     def launches(self):
         return self.lib.launches

@@ -36,6 +36,7 @@
 //    (12 warps x 2 x 2 KB = 48 KB per SM; one row gives 3.5 TB/s);
 //  * tasks (strip, segment) are numbered with the segment fastest and dealt to the warps round-robin, so that at any
 //    time the GPU sweeps a few consecutive grid rows and the CTAs' 768-byte pieces are adjacent in every column.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -235,6 +236,269 @@ __global__ void __launch_bounds__(GT, 1)
   for (int e = threadIdx.x; e < NBLK * 64; e += GT) partials[(int64_t)blockIdx.x * NBLK * 64 + e] = red[e];
 }
 
+
+// ---- version 3: TMA-staged row slots (tensor maps), warp-specialised ----------------------------------------------------
+// One producer warp (lane 0) streams grid rows of a (TI x 64) task through a ring of shared-memory slots with
+// cp.async.bulk.tensor: one 3-D box {72 j, 1 row, 8 NB columns} of V, one 2-D box each of y and e^u, all completing on
+// the slot's `full` mbarrier.  Out-of-range j (j0 - 4 < 0, j0 + 68 > m) is zero-filled by the TMA unit = the Dirichlet
+// condition.  Eight consumer warps each own an 8-point j-segment, keep the (up, mid, dn) window of their fragment in
+// registers, take left/right neighbours and e^u from the mid row's slot, apply the stencil (apply_refbits, bit-identical
+// to apply_kernel), store J V and feed the Gram DMMAs.  A slot is released (`empty`, one arrival per consumer warp)
+// when its row has been the mid row.  Plane stride 576 B = 64 mod 128: the quarter-warp's two 64-byte pieces of an
+// LDS.128 fall into disjoint banks.
+namespace v3 {
+// CW consumer warps -> TJ = 8 CW grid points per row slot; plane = TJ + 8 doubles (j0 - 4 .. j0 + TJ + 3); for CW = 8,
+// 12, 16 the plane stride is 576 / 832 / 1088 bytes = 64 mod 128
+template <int CW> __host__ __device__ constexpr int plane_bytes() { return (8 * CW + 8) * 8; }
+template <int CW> __host__ __device__ constexpr int ye_bytes() { return (plane_bytes<CW>() + 127) / 128 * 128; }
+template <int NB, int CW> __host__ __device__ constexpr int slot_bytes() { return 8 * NB * plane_bytes<CW>() + 2 * ye_bytes<CW>(); }
+template <int NB, int CW> __host__ __device__ constexpr int nslot() {
+  return (200 * 1024 / slot_bytes<NB, CW>()) < 16 ? (200 * 1024 / slot_bytes<NB, CW>()) : 16;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ double2 lds2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds1(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
+template <int NB, bool STORE, int CW>
+__global__ void __launch_bounds__(32 * (CW + 1), 1)
+    stencil_gram_tma(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmY,
+                     const __grid_constant__ CUtensorMap tmE, Problem p, int TI, double* __restrict__ JV,
+                     double* __restrict__ partials) {
+  constexpr int NBLK = nblocks(NB);
+  constexpr int SB = slot_bytes<NB, CW>();
+  constexpr int NS = nslot<NB, CW>();
+  constexpr int TJ = 8 * CW, PB = plane_bytes<CW>(), YE = ye_bytes<CW>();
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(16) double red[NBLK * 64];
+  __shared__ __align__(8) unsigned long long bars[2 * NS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m = p.m;
+  const int ntj = (m + TJ - 1) / TJ;
+  const int nstrip = (p.rows + TI - 1) / TI;
+  const int64_t ntask = (int64_t)ntj * nstrip;
+  const uint32_t ring0 = smem_u32(ring), full0 = smem_u32(bars), empty0 = full0 + 8 * NS;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, CW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc[NBLK][2];
+#pragma unroll
+  for (int b = 0; b < NBLK; ++b) acc[b][0] = acc[b][1] = 0.0;
+
+  if (warp == CW) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t task = blockIdx.x; task < ntask; task += gridDim.x) {
+        const int strip = (int)(task / ntj), tj = (int)(task - (int64_t)strip * ntj);
+        const int i0 = strip * TI, i1 = min(i0 + TI, p.rows), j0 = tj * TJ;
+        for (int r = i0 - 1; r <= i1; ++r, ++it) {
+          const uint32_t s = it % NS, ph = (it / NS) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const uint32_t dst = ring0 + s * SB, fb = full0 + 8 * s;
+          mbar_expect_tx(fb, (8 * NB + 2) * PB);
+          tma_load_3d(dst, &tmV, j0 - 4, r + 2, 0, fb);
+          tma_load_2d(dst + 8 * NB * PB, &tmY, j0 - 4, r + 2, fb);
+          tma_load_2d(dst + 8 * NB * PB + YE, &tmE, j0 - 4, r + 2, fb);
+        }
+      }
+    }
+  } else {
+    const double d0 = __dadd_rn(4.0 * p.c_lap, -p.c_adv), cd = __dadd_rn(-p.c_lap, p.c_adv), cu = -p.c_lap, cl = -p.c_lap;
+    // per column block: byte offset of this lane's pair inside a slot, and what the column is
+    uint32_t poff[NB];
+    int kind[NB];  // 0: stencil column, 1: the y column (copied), 2: beyond the panel (zeros)
+#pragma unroll
+    for (int I = 0; I < NB; ++I) {
+      const int col = 8 * I + g;
+      kind[I] = col < p.k ? 0 : (col == p.k ? 1 : 2);
+      poff[I] = (uint32_t)((col < p.k ? col * PB : (col == p.k ? 8 * NB * PB : 0)) + 8 * (4 + 8 * warp + 2 * t));
+    }
+    const uint32_t eoff = (uint32_t)(8 * NB * PB + YE + 8 * (4 + 8 * warp + 2 * t));
+    uint32_t it = 0;
+    for (int64_t task = blockIdx.x; task < ntask; task += gridDim.x) {
+      const int strip = (int)(task / ntj), tj = (int)(task - (int64_t)strip * ntj);
+      const int i0 = strip * TI, i1 = min(i0 + TI, p.rows);
+      const int j = tj * TJ + 8 * warp + 2 * t;
+      const bool active = tj * TJ + 8 * warp < m;  // the last tile of a row may be narrower than TJ (whole segments)
+      double2 up[NB], mid[NB], dn[NB];
+      {  // row i0 - 1
+        const uint32_t s = it % NS, ph = (it / NS) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        const uint32_t base = ring0 + s * SB;
+#pragma unroll
+        for (int I = 0; I < NB; ++I) up[I] = lds2(base + poff[I]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        ++it;
+      }
+      uint32_t mid_base, mid_slot;
+      {  // row i0
+        const uint32_t s = it % NS, ph = (it / NS) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        mid_base = ring0 + s * SB;
+        mid_slot = s;
+#pragma unroll
+        for (int I = 0; I < NB; ++I) mid[I] = lds2(mid_base + poff[I]);
+        ++it;
+      }
+      for (int i = i0; i < i1; ++i) {
+        const uint32_t s = it % NS, ph = (it / NS) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        const uint32_t base = ring0 + s * SB;
+#pragma unroll
+        for (int I = 0; I < NB; ++I) dn[I] = lds2(base + poff[I]);
+        ++it;
+        // neighbours and e^u of the mid row, then give its slot back
+        double lf[NB], rt[NB];
+#pragma unroll
+        for (int I = 0; I < NB; ++I) {
+          lf[I] = lds1(mid_base + poff[I] - 8);
+          rt[I] = lds1(mid_base + poff[I] + 16);
+        }
+        const double2 e = lds2(mid_base + eoff);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);
+        const double dga = __dadd_rn(d0, __dmul_rn(p.lam, e.x)), dgb = __dadd_rn(d0, __dmul_rn(p.lam, e.y));
+        const int64_t ro = (int64_t)i * m + j;
+        double2 tile[NB];
+#pragma unroll
+        for (int I = 0; I < NB; ++I) {
+          if (kind[I] == 0 && active) {
+            const double oa = apply_refbits(cu, cl, dga, cd, up[I].x, lf[I], mid[I].x, mid[I].y, dn[I].x);
+            const double obv = apply_refbits(cu, cl, dgb, cd, up[I].y, mid[I].x, mid[I].y, rt[I], dn[I].y);
+            tile[I] = make_double2(p.sign * oa, p.sign * obv);
+            if (STORE) __stcs(reinterpret_cast<double2*>(JV + (int64_t)(8 * I + g) * p.ldjv + ro), tile[I]);
+          } else if (kind[I] == 1 && active) {
+            tile[I] = mid[I];
+          } else {
+            tile[I] = make_double2(0.0, 0.0);
+          }
+        }
+#pragma unroll
+        for (int I = 0; I < NB; ++I)
+#pragma unroll
+          for (int J = I; J < NB; ++J) {
+            const int b = blk_index(NB, I, J);
+            dmma(acc[b][0], acc[b][1], tile[I].x, tile[J].x);
+            dmma(acc[b][0], acc[b][1], tile[I].y, tile[J].y);
+          }
+#pragma unroll
+        for (int I = 0; I < NB; ++I) {
+          up[I] = mid[I];
+          mid[I] = dn[I];
+        }
+        mid_base = base;
+        mid_slot = s;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);  // row i1 was only ever a dn row
+    }
+  }
+  // CTA sum in warp order (consumer warps), one partial per CTA in fragment order
+  for (int w = 0; w < CW; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        double2* q = reinterpret_cast<double2*>(red + b * 64 + lane * 2);
+        double2 v = make_double2(acc[b][0], acc[b][1]);
+        if (w > 0) {
+          v.x += q->x;
+          v.y += q->y;
+        }
+        *q = v;
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < NBLK * 64; e += blockDim.x) partials[(int64_t)blockIdx.x * NBLK * 64 + e] = red[e];
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    if (!f || q != cudaDriverEntryPointSuccess) {
+      printf("cuTensorMapEncodeTiled not available\n");
+      exit(1);
+    }
+    fn = (EncodeFn)f;
+  }
+  return fn;
+}
+// stored columns: [rows + 4][m] doubles, column stride ld; box {PW, 1, ncol_box}
+static CUtensorMap make_map(const double* base, int m, int rows, int64_t ld, int ncols, int ncol_box, int PW) {
+  CUtensorMap tm;
+  if (ncols > 1 || ncol_box > 1) {
+    cuuint64_t dims[3] = {(cuuint64_t)m, (cuuint64_t)(rows + 4), (cuuint64_t)ncols};
+    cuuint64_t strides[2] = {(cuuint64_t)m * 8, (cuuint64_t)ld * 8};
+    cuuint32_t box[3] = {(cuuint32_t)PW, 1, (cuuint32_t)ncol_box};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled(3d) failed: %d\n", (int)r); exit(1); }
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)(rows + 4)};
+    cuuint64_t strides[1] = {(cuuint64_t)m * 8};
+    cuuint32_t box[2] = {(cuuint32_t)PW, 1};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled(2d) failed: %d\n", (int)r); exit(1); }
+  }
+  return tm;
+}
+}  // namespace v3
+
 // fragment order -> dense c x c (upper part), CTA partials added in CTA order
 __global__ void gather_kernel(const double* partials, int nctas, int NB, int c, double* G) {
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -262,6 +526,35 @@ float run_fused(const Problem& p, const double* V, const double* expu, const dou
     gather_kernel<<<1, 1024>>>(partials, ctas, NB, p.k + 1, G);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (r >= 2 && ms < best) best = ms;
+  }
+  return best;
+}
+
+template <int NB, bool STORE, int CW>
+float run_tma(const Problem& p, const double* V, const double* expu, const double* y, double* JV, double* partials,
+              double* G, int ctas, int reps, int TI) {
+  using namespace v3;
+  constexpr int PW = 8 * CW + 8;
+  const CUtensorMap tmV = make_map(V, p.m, p.rows, p.ldv, p.k, 8 * NB, PW);
+  const CUtensorMap tmY = make_map(y, p.m, p.rows, p.ldv, 1, 1, PW);
+  const CUtensorMap tmE = make_map(expu, p.m, p.rows, p.ldv, 1, 1, PW);
+  auto kern = stencil_gram_tma<NB, STORE, CW>;
+  const int dyn = slot_bytes<NB, CW>() * nslot<NB, CW>();
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int r = 0; r < reps + 2; ++r) {
+    CK(cudaEventRecord(e0));
+    kern<<<ctas, 32 * (CW + 1), dyn>>>(tmV, tmY, tmE, p, TI, JV, partials);
+    gather_kernel<<<1, 1024>>>(partials, ctas, NB, p.k + 1, G);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     if (r >= 2 && ms < best) best = ms;
@@ -318,7 +611,27 @@ int main(int argc, char** argv) {
 
   const int variant = argc > 3 ? atoi(argv[3]) : 1;  // 1 = version 1 (measured), 2 = version 2 (shuffle neighbours)
   float ms = 0;
-  if (variant == 2) {
+  const int TI = argc > 4 ? atoi(argv[4]) : 64;
+  if (variant == 3 || variant == 4) {  // 3: TMA-staged, stores J V; 4: the same without the store (Gram only)
+    if (m % 8) {
+      printf("version 3 needs m %% 8 == 0\n");
+      return 1;
+    }
+    const int cw = argc > 5 ? atoi(argv[5]) : 8;
+    printf("consumer warps %d: ", cw);
+#define RUN_TMA(NBV, ST)                                                                  \
+  if (NB == NBV) {                                                                        \
+    if (cw == 12) ms = run_tma<NBV, ST, 12>(p, V, E, Y, JV, part, G, ctas, 5, TI);        \
+    else if (cw == 10) ms = run_tma<NBV, ST, 10>(p, V, E, Y, JV, part, G, ctas, 5, TI);   \
+    else if (cw == 16) ms = run_tma<NBV, ST, 16>(p, V, E, Y, JV, part, G, ctas, 5, TI);   \
+    else ms = run_tma<NBV, ST, 8>(p, V, E, Y, JV, part, G, ctas, 5, TI);                  \
+  }
+    if (variant == 3) {
+      RUN_TMA(1, true) RUN_TMA(2, true) RUN_TMA(3, true) RUN_TMA(4, true)
+    } else {
+      RUN_TMA(1, false) RUN_TMA(2, false) RUN_TMA(3, false) RUN_TMA(4, false)
+    }
+  } else if (variant == 2) {
     if (NB == 1) ms = run_fused<1, true>(p, V, E, Y, JV, part, G, ctas, 5);
     if (NB == 2) ms = run_fused<2, true>(p, V, E, Y, JV, part, G, ctas, 5);
     if (NB == 3) ms = run_fused<3, true>(p, V, E, Y, JV, part, G, ctas, 5);
@@ -330,7 +643,7 @@ int main(int argc, char** argv) {
     if (NB == 4) ms = run_fused<4, false>(p, V, E, Y, JV, part, G, ctas, 5);
   }
   const double bytes = 16.0 * n * k + 16.0 * n;  // read V, write J V, read e^u and y
-  printf("fused stencil + Gram v%d  m=%d k=%d  %.4f ms  %.1f GB/s over %.3f GB\n", variant == 2 ? 2 : 1, m, k, ms, bytes / ms / 1e6, bytes / 1e9);
+  printf("fused stencil + Gram v%d  m=%d k=%d TI=%d  %.4f ms  %.1f GB/s over %.3f GB (16nk+16n)\n", variant, m, k, TI, ms, bytes / ms / 1e6, bytes / 1e9);
 
   if (m <= 1024) {  // validation against the naive kernels
     CK(cudaMalloc(&JVr, sizeof(double) * (size_t)k * p.ldjv));
