@@ -225,12 +225,6 @@ class BratuDevice:
         _lib.check(rt.lib.gnk_stencil_apply(rt.ctx, C.byref(self.lay), C.byref(self.prm), ptr(expu), ptr(inp), in_ld, k,
                                             sign, transpose, ptr(out), out_ld, out_off, rt.stream), "gnk_stencil_apply")
 
-    def tsqr_fused(self, expu, V, ldv, k, r, sign_a, out):
-        """projected least squares with J V_k formed inside the TSQR leaf (never stored)"""
-        rt = self.rt
-        _lib.check(rt.lib.gnk_tsqr_ls_stencil(rt.ctx, C.byref(self.lay), C.byref(self.prm), ptr(expu), ptr(V), ldv, k,
-                                              ptr(r), float(sign_a), ptr(out), rt.stream), "gnk_tsqr_ls_stencil")
-
     def halo_exchange(self, col, depth, offset=0):
         rt = self.rt
         if rt.world > 1:

@@ -134,24 +134,16 @@ __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_brat
 // out[:, col] = sign * Op * in[:, col];  grid = (k, j-tiles, row-tiles): the column index is the
 // fastest block coordinate so that the CTAs sharing one e^u tile are co-resident and the tile is
 // served from L2 after its first HBM read.
-// DOTS: the same pass also forms h[col] = in[:, col] . w over the owned rows (first half of krylow.py:64): the
-// Gram-Schmidt coefficients against V_k and the next outer iteration's J V_k both stream V_k once, and w (like e^u)
-// is shared by the k CTAs of a tile, so it costs one HBM read.  Per-CTA partial sums are reduced by the CTA that
-// arrives last, in a fixed order (deterministic).
-template <bool VEC, bool DOTS>
+template <bool VEC>
 __global__ void __launch_bounds__(TPBX) apply_kernel(gnk_layout lay, gnk_bratu prm, const double* __restrict__ expu,
                                                       const double* __restrict__ in, int64_t in_ld, double sign,
                                                       int transpose, int TR, double* __restrict__ out,
-                                                      int64_t out_ld, int64_t out_off, const double* __restrict__ w,
-                                                      double* __restrict__ partials, unsigned int* ticket,
-                                                      double* __restrict__ h) {
+                                                      int64_t out_ld, int64_t out_off) {
   constexpr int W = VEC ? 2 : 1;
   const int m = lay.m;
   const int col = blockIdx.x;
   const int j0 = W * (blockIdx.y * TPBX + threadIdx.x);
-  double acc = 0.0;
-  if (!DOTS && j0 >= m) return;
-  if (j0 < m) {
+  if (j0 >= m) return;
   const int rbeg = (int)blockIdx.z * TR;
   const int rend = min(rbeg + TR, lay.rows);
   const double* vb = in + (int64_t)col * in_ld + lay.off + j0;
@@ -181,29 +173,8 @@ __global__ void __launch_bounds__(TPBX) apply_kernel(gnk_layout lay, gnk_bratu p
     const double oa = apply_refbits(cu, cl, dga, cd, up.a, lf, mid.a, ra, dn.a);
     const double ob2 = VEC ? apply_refbits(cu, cl, dgb, cd, up.b, mid.a, mid.b, rt, dn.b) : 0.0;
     store_pair<VEC>(ob + ro, sign * oa, sign * ob2);
-    if (DOTS) {
-      Pair<VEC> wv = load_pair<VEC>(w + lay.off + j0 + ro);
-      acc = fma(mid.a, wv.a, acc);
-      if (VEC) acc = fma(mid.b, wv.b, acc);
-    }
     up = mid;
     mid = dn;
-  }
-  }
-  if (DOTS) {
-    __shared__ double sh[32];
-    acc = block_sum(acc, sh);
-    const unsigned int nb = gridDim.y * gridDim.z;
-    if (threadIdx.x == 0) partials[(size_t)col * nb + blockIdx.y * gridDim.z + blockIdx.z] = acc;
-    if (grid_arrive_last(ticket)) {
-      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-      for (int j = wid; j < (int)gridDim.x; j += nw) {
-        double a = 0.0;
-        for (unsigned int b = lane; b < nb; b += 32) a += __ldcg(partials + (size_t)j * nb + b);
-        a = warp_sum(a);
-        if (lane == 0) h[j] = a;
-      }
-    }
   }
 }
 
@@ -239,114 +210,6 @@ __global__ void __launch_bounds__(TPBX) normal_diag_kernel(gnk_layout lay, gnk_b
   }
 }
 
-
-// Gram-Schmidt update fused with the next iteration's SpMM (krylow.py:64 second half + gauss_newton_krylow.py:86):
-//   w -= V_k h   and, in the same pass over V_k,   JV[:, j] = sign * (M V[:, j]),  M = L + alpha D + lam diag(e^u).
-// The update pass streams every basis column anyway, and J(x_new) is already known when the basis is expanded, so
-// the projected operator of the NEXT outer iteration costs no extra read of V_k (-8nk bytes per iteration).
-// One CTA owns an 8-row x 256-column tile and walks the k columns; per column a 3-row register window marches down
-// the tile (rows above/below the tile are re-read, they hit L2).  Arithmetic is identical to apply_kernel /
-// update_kernel (same products, same order), so the results are bit-for-bit those of the two separate kernels.
-constexpr int UTR = 8;
-template <bool VEC>
-__global__ void __launch_bounds__(TPBX) update_apply_kernel(gnk_layout lay, gnk_bratu prm,
-                                                             const double* __restrict__ expu,
-                                                             const double* __restrict__ V, int64_t ldv, int k,
-                                                             const double* __restrict__ h, double* __restrict__ w,
-                                                             double sign, double* __restrict__ JV, int64_t ldjv,
-                                                             double* __restrict__ partials, unsigned int* ticket,
-                                                             double* __restrict__ stats) {
-  __shared__ double coef[GNK_MAX_BASIS];
-  __shared__ double sh[32];
-  constexpr int W = VEC ? 2 : 1;
-  for (int j = threadIdx.x; j < k; j += blockDim.x) coef[j] = h[j];
-  __syncthreads();
-  const int m = lay.m;
-  const int j0 = W * (blockIdx.x * TPBX + threadIdx.x);
-  const int rbeg = (int)blockIdx.y * UTR;
-  const int nr = min(UTR, lay.rows - rbeg);
-  double ss = 0.0, mx = 0.0;
-  if (j0 < m) {
-    const bool has_l = j0 > 0, has_r = (j0 + W) < m;
-    const double d0 = __dadd_rn(4.0 * prm.c_lap, -prm.c_adv);
-    const double cd = __dadd_rn(-prm.c_lap, prm.c_adv);
-    const double cu = -prm.c_lap, cl = -prm.c_lap;
-    double dga[UTR], dgb[UTR], acca[UTR], accb[UTR];
-#pragma unroll
-    for (int i = 0; i < UTR; ++i) {
-      dga[i] = d0;
-      dgb[i] = d0;
-      acca[i] = 0.0;
-      accb[i] = 0.0;
-      if (expu && i < nr) {
-        Pair<VEC> e = load_pair<VEC>(expu + lay.off + (int64_t)(rbeg + i) * m + j0);
-        dga[i] = __dadd_rn(d0, __dmul_rn(prm.lam, e.a));
-        dgb[i] = __dadd_rn(d0, __dmul_rn(prm.lam, e.b));
-      }
-    }
-    for (int col = 0; col < k; ++col) {
-      const double* vb = V + (int64_t)col * ldv + lay.off + j0;
-      double* ob = JV + (int64_t)col * ldjv + j0;
-      const double hj = coef[col];
-      Pair<VEC> up = load_pair<VEC>(vb + (int64_t)(rbeg - 1) * m);
-      Pair<VEC> mid = load_pair<VEC>(vb + (int64_t)rbeg * m);
-#pragma unroll
-      for (int i = 0; i < UTR; ++i) {
-        if (i < nr) {
-          const int64_t ro = (int64_t)(rbeg + i) * m;
-          Pair<VEC> dn = load_pair<VEC>(vb + ro + m);
-          const double lf = has_l ? vb[ro - 1] : 0.0;
-          const double rt = has_r ? vb[ro + W] : 0.0;
-          const double ra = VEC ? mid.b : rt;
-          const double oa = apply_refbits(cu, cl, dga[i], cd, up.a, lf, mid.a, ra, dn.a);
-          const double ob2 = VEC ? apply_refbits(cu, cl, dgb[i], cd, up.b, mid.a, mid.b, rt, dn.b) : 0.0;
-          store_pair<VEC>(ob + ro, sign * oa, sign * ob2);
-          acca[i] = fma(mid.a, hj, acca[i]);
-          if (VEC) accb[i] = fma(mid.b, hj, accb[i]);
-          up = mid;
-          mid = dn;
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < UTR; ++i) {
-      if (i < nr) {
-        double* wp = w + lay.off + (int64_t)(rbeg + i) * m + j0;
-        Pair<VEC> wv = load_pair<VEC>(wp);
-        wv.a -= acca[i];
-        if (VEC) wv.b -= accb[i];
-        store_pair<VEC>(wp, wv.a, wv.b);
-        ss = fma(wv.a, wv.a, ss);
-        mx = fmax(mx, fabs(wv.a));
-        if (VEC) {
-          ss = fma(wv.b, wv.b, ss);
-          mx = fmax(mx, fabs(wv.b));
-        }
-      }
-    }
-  }
-  ss = block_sum(ss, sh);
-  mx = block_max(mx, sh);
-  const unsigned int bid = linear_block_id();
-  if (threadIdx.x == 0) {
-    partials[2 * bid] = ss;
-    partials[2 * bid + 1] = mx;
-  }
-  if (grid_arrive_last(ticket)) {
-    double a = 0.0, b = 0.0;
-    const unsigned int nb = total_blocks();
-    for (unsigned int i = threadIdx.x; i < nb; i += blockDim.x) {
-      a += __ldcg(partials + 2 * i);
-      b = fmax(b, __ldcg(partials + 2 * i + 1));
-    }
-    a = block_sum(a, sh);
-    b = block_max(b, sh);
-    if (threadIdx.x == 0) {
-      stats[0] = a;
-      stats[1] = b;
-    }
-  }
-}
 
 // Rows per CTA strip.  A strip re-reads one halo row above and below (from L2), so taller is cheaper per row, but
 // the grid should fill whole waves of resident CTAs (8 x 128 threads per SM at <= 64 registers): a 1.7-wave grid
@@ -426,13 +289,11 @@ int gnk_stencil_apply(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm,
   GNK_REQUIRE(grid.z <= 65535, "gnk_stencil_apply: too many row tiles");
   const double* e = (prm->lam == 0.0) ? nullptr : d_expu;
   if (vec)
-    apply_kernel<true, false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr,
-                                                                     d_out, out_ld, out_off, nullptr, nullptr, nullptr,
-                                                                     nullptr);
+    apply_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr, d_out,
+                                                              out_ld, out_off);
   else
-    apply_kernel<false, false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr,
-                                                                      d_out, out_ld, out_off, nullptr, nullptr, nullptr,
-                                                                      nullptr);
+    apply_kernel<false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr, d_out,
+                                                               out_ld, out_off);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -451,65 +312,6 @@ int gnk_stencil_normal_diag(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu
     normal_diag_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, tr, d_out);
   else
     normal_diag_kernel<false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, tr, d_out);
-  GNK_LAUNCH_CHECK(ctx);
-  return 0;
-}
-
-int gnk_stencil_apply_dots(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
-                           const double* d_V, int64_t ldv, int k, double sign, double* d_JV, int64_t ldjv,
-                           const double* d_w, double* d_h, void* stream) {
-  GNK_REQUIRE(ctx && prm && d_V && d_JV && d_w && d_h, "gnk_stencil_apply_dots: null argument");
-  GNK_REQUIRE(check_layout(lay) == 0, "gnk_stencil_apply_dots: inconsistent stencil layout");
-  GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_stencil_apply_dots: k out of range");
-  GNK_REQUIRE(prm->lam == 0.0 || d_expu, "gnk_stencil_apply_dots: e^u diagonal required when lam != 0");
-  const bool vec = (lay->m % 2) == 0 && (ldv % 2) == 0 && (ldjv % 2) == 0 && (lay->ld % 2) == 0;
-  const int gx = (int)ceil_div(lay->m, (vec ? 2 : 1) * TPBX);
-  const int tr = pick_tr(ctx, gx, lay->rows, k);
-  dim3 grid(k, gx, (unsigned)ceil_div(lay->rows, tr));
-  GNK_REQUIRE(grid.z <= 65535, "gnk_stencil_apply_dots: too many row tiles");
-  const size_t need = sizeof(double) * (size_t)GNK_MAX_BASIS * grid.y * grid.z;
-  if (need > ctx->apart_bytes) {
-    GNK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    if (ctx->d_apart) GNK_CUDA(cudaFree(ctx->d_apart));
-    ctx->d_apart = nullptr;
-    ctx->apart_bytes = 0;
-    GNK_CUDA(cudaMalloc(&ctx->d_apart, need));
-    ctx->apart_bytes = need;
-  }
-  const double* e = (prm->lam == 0.0) ? nullptr : d_expu;
-  if (vec)
-    apply_kernel<true, true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_V, ldv, sign, 0, tr, d_JV, ldjv, 0,
-                                                                    d_w, ctx->d_apart, ctx->d_tickets + TK_APPLY_DOTS,
-                                                                    d_h);
-  else
-    apply_kernel<false, true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_V, ldv, sign, 0, tr, d_JV, ldjv,
-                                                                     0, d_w, ctx->d_apart,
-                                                                     ctx->d_tickets + TK_APPLY_DOTS, d_h);
-  GNK_LAUNCH_CHECK(ctx);
-  return 0;
-}
-
-int gnk_cgs_update_spmm(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
-                        const double* d_V, int k, const double* d_h, double* d_w, double* d_stats, double sign,
-                        double* d_JV, int64_t ldjv, void* stream) {
-  GNK_REQUIRE(ctx && prm && d_V && d_h && d_w && d_stats && d_JV, "gnk_cgs_update_spmm: null argument");
-  GNK_REQUIRE(check_layout(lay) == 0, "gnk_cgs_update_spmm: inconsistent stencil layout");
-  GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_update_spmm: k out of range");
-  GNK_REQUIRE(prm->lam == 0.0 || d_expu, "gnk_cgs_update_spmm: e^u diagonal required when lam != 0");
-  const bool vec = (lay->m % 2) == 0 && (lay->ld % 2) == 0 && (ldjv % 2) == 0;
-  const int gx = (int)ceil_div(lay->m, (vec ? 2 : 1) * TPBX);
-  dim3 grid(gx, (unsigned)ceil_div(lay->rows, UTR));
-  GNK_REQUIRE((int64_t)grid.x * grid.y * 2 <= 65536, "gnk_cgs_update_spmm: grid exceeds the partials scratch");
-  const double* e = (prm->lam == 0.0) ? nullptr : d_expu;
-  double* part = ctx->d_partials + PART_RESID;
-  if (vec)
-    update_apply_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_V, lay->ld, k, d_h, d_w, sign,
-                                                                     d_JV, ldjv, part, ctx->d_tickets + TK_UPDATE,
-                                                                     d_stats);
-  else
-    update_apply_kernel<false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_V, lay->ld, k, d_h, d_w, sign,
-                                                                      d_JV, ldjv, part, ctx->d_tickets + TK_UPDATE,
-                                                                      d_stats);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -25,6 +25,7 @@
 // against ~c^2 dependent DFMAs per row; two reads of the panel (16 n c bytes).  Multi-GPU: the Gram matrices are summed
 // over the ranks in rank order inside the single-CTA factor kernels (peer-mailbox all-reduce, bit-identical decisions
 // on every rank), replacing the TSQR triangle gather and the tree levels.
+#include <cuda.h>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -68,12 +69,14 @@ __device__ __forceinline__ double2 load_pair(const double* p, int64_t r, int64_t
 // Sum the per-warp fragment accumulators of a CTA in warp order, publish the CTA's partial, and let the CTA that
 // arrives last add the partials of all CTAs in CTA order (deterministic).  NE = doubles per Gram matrix in fragment
 // order: block (I <= J) * 64 + lane * 2 + {0, 1}  <->  G[8 I + g][8 J + 2 t + {0, 1}].
-template <int NBLK>
+// NW = warps of the CTA that hold accumulators (the first NW warps), NT = threads of the CTA (all take part in the
+// barriers and the copies).
+template <int NBLK, int NW = GW, int NT = GT>
 __device__ __forceinline__ void reduce_gram(double (&acc)[NBLK][2], double* red, double* __restrict__ partials,
                                             unsigned int* ticket, double* __restrict__ Gout) {
   constexpr int NE = NBLK * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int w = 0; w < GW; ++w) {
+  for (int w = 0; w < NW; ++w) {
     if (warp == w) {
 #pragma unroll
       for (int b = 0; b < NBLK; ++b) {
@@ -90,11 +93,11 @@ __device__ __forceinline__ void reduce_gram(double (&acc)[NBLK][2], double* red,
     __syncthreads();
   }
   double* mine = partials + (int64_t)blockIdx.x * NE;
-  for (int e = threadIdx.x; e < NE; e += GT) mine[e] = red[e];
+  for (int e = threadIdx.x; e < NE; e += NT) mine[e] = red[e];
   __threadfence();  // every thread publishes its own stores before the CTA takes its ticket
   if (!grid_arrive_last(ticket)) return;
   const int nb = gridDim.x;
-  for (int e = threadIdx.x; e < NE; e += GT) {
+  for (int e = threadIdx.x; e < NE; e += NT) {
     double s = 0.0;
     int b = 0;
     for (; b + 4 <= nb; b += 4) {
@@ -680,13 +683,18 @@ int launch_refine(gnk_ctx* ctx, const PanelSource& src, double sign, double* bas
   return 0;
 }
 
-template <int NB, int RU>
-int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k, const double* d_y, double sign,
-               double* d_out, cudaStream_t st) {
+int ensure_scratch(gnk_ctx* ctx, cudaStream_t st) {
   if (!ctx->d_cholqr) {
     GNK_CUDA(cudaMalloc(&ctx->d_cholqr, sizeof(double) * CQ_TOTAL));
     GNK_CUDA(cudaMemsetAsync(ctx->d_cholqr, 0, sizeof(double) * CQ_TOTAL, st));
   }
+  return 0;
+}
+
+// Everything after pass 1: this rank's Gram matrix of [A | y] (fragment order) is at base + CQ_LOCAL.
+template <int NB, int RU>
+int cholqr_tail(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k, const double* d_y, double sign,
+                double* d_out, cudaStream_t st) {
   double* base = ctx->d_cholqr;
   int* status = reinterpret_cast<int*>(base + CQ_STATUS);
   PanelSource src{d_A, lda, d_y, k, n_rows};
@@ -700,11 +708,6 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
   GNK_REQUIRE(ctx->nranks <= P2P_MAXR, "cholqr: more ranks than the Gram gather buffer holds");
   static const int refine_on = getenv("GNK_LS_REFINE") ? atoi(getenv("GNK_LS_REFINE")) : 1;
   const int method = (ctx->ls_method == 2 || !refine_on) ? 2 : 0;
-
-  // pass 1 and its factorisation
-  cholqr_gram_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_PART,
-                                                        ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
-  GNK_LAUNCH_CHECK(ctx);
   // with the peer mailboxes attached the factor kernels (single CTAs) run the cross-rank sum themselves
   const gnk_p2p_dev none{nullptr, 0, 1, 0ull};
   const gnk_p2p_dev pd1 = multi ? p2p_next(ctx) : none;
@@ -738,6 +741,357 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
   return 0;
 }
 
+template <int NB, int RU>
+int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k, const double* d_y, double sign,
+               double* d_out, cudaStream_t st) {
+  if (int rc = ensure_scratch(ctx, st)) return rc;
+  double* base = ctx->d_cholqr;
+  PanelSource src{d_A, lda, d_y, k, n_rows};
+  constexpr int64_t GRAN = (int64_t)CH * RU * GW;
+  int64_t ctas = ctx->sm_count < CQ_MAX_CTAS ? ctx->sm_count : CQ_MAX_CTAS;
+  if (ctas * GRAN > n_rows) ctas = ceil_div(n_rows, GRAN);
+  const int64_t rows_per_cta = ceil_div(ceil_div(n_rows, ctas), GRAN) * GRAN;
+  ctas = ceil_div(n_rows, rows_per_cta);
+  // pass 1 and its factorisation
+  cholqr_gram_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_PART,
+                                                        ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
+  GNK_LAUNCH_CHECK(ctx);
+  return cholqr_tail<NB, RU>(ctx, d_A, lda, n_rows, k, d_y, sign, d_out, st);
+}
+
+// ======================================================================================================================
+// Pass 1 fused with the projected operator: J V_k (gauss_newton_krylow.py:86) is formed from the basis, WRITTEN for the
+// second pass, and its Gram matrix with the residual accumulated in the same sweep -- the least-squares panel is read
+// once instead of being written by the SpMM, read by pass 1 and read again by pass 2 (24 n k -> 16 n k + 8 n k).
+//
+// Warp-specialised, TMA-staged (measured stand-alone in tools/microbench_stencil_gram.cu, version 3):
+//  * a task is TI grid rows x TJ = 8 CW grid points; one producer warp (lane 0) streams its rows through a ring of
+//    shared-memory slots with cp.async.bulk.tensor: a 3-D box {TJ + 8 points, 1 row, 8 NB columns} of the basis and a
+//    2-D box each of the residual and of e^u, all completing on the slot's `full` mbarrier.  Out-of-range j (j0 - 4 < 0,
+//    j0 + TJ + 4 > m) is zero-filled by the TMA unit, which IS the Dirichlet condition; halo rows are stored;
+//  * CW consumer warps own one 8-point segment each.  Lane (g, t) holds grid points 2t, 2t+1 of basis column 8 I + g
+//    -- the DMMA fragment of cholqr_gram_kernel -- keeps the (up, mid, dn) rows of that fragment in registers, reads
+//    the left / right neighbours and e^u from the mid row's slot, applies the stencil with apply_refbits (scipy's
+//    rounding order: J V is bit-identical to gnk_stencil_apply), stores J V and feeds the Gram DMMAs;
+//  * a slot goes back to the producer (`empty`, one arrival per consumer warp) once its row has been the mid row;
+//  * plane stride (TJ + 8) * 8 bytes = 64 mod 128 for CW = 8, 10, 12: the two 64-byte pieces a quarter-warp reads with
+//    one LDS.128 fall into disjoint banks.
+// ======================================================================================================================
+struct StencilPanel {
+  int m, rows, k;       // row length, owned grid rows, basis columns
+  int has_e;            // 0: lam == 0, no e^u plane
+  int64_t ldjv;
+  double c_lap, c_adv, lam, sign;
+};
+
+template <int CW> __host__ __device__ constexpr int sg_plane_bytes() { return (8 * CW + 8) * 8; }
+template <int CW> __host__ __device__ constexpr int sg_ye_bytes() { return (sg_plane_bytes<CW>() + 127) / 128 * 128; }
+template <int NB, int CW> __host__ __device__ constexpr int sg_slot_bytes() {
+  return 8 * NB * sg_plane_bytes<CW>() + 2 * sg_ye_bytes<CW>();
+}
+template <int NB, int CW> __host__ __device__ constexpr int sg_nslot() {
+  return (200 * 1024 / sg_slot_bytes<NB, CW>()) < 16 ? (200 * 1024 / sg_slot_bytes<NB, CW>()) : 16;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ double2 lds2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds1(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
+template <int NB, int CW>
+__global__ void __launch_bounds__(32 * (CW + 1), 1)
+    stencil_gram_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmY,
+                        const __grid_constant__ CUtensorMap tmE, StencilPanel p, int TI, double* __restrict__ JV,
+                        double* __restrict__ partials, unsigned int* ticket, double* __restrict__ Gout) {
+  constexpr int NBLK = nblocks(NB);
+  constexpr int SB = sg_slot_bytes<NB, CW>();
+  constexpr int NS = sg_nslot<NB, CW>();
+  constexpr int TJ = 8 * CW, PB = sg_plane_bytes<CW>(), YE = sg_ye_bytes<CW>();
+  constexpr int NT = 32 * (CW + 1);
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(16) double red[NBLK * 64];
+  __shared__ __align__(8) unsigned long long bars[2 * NS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m = p.m;
+  const int ntj = (m + TJ - 1) / TJ;
+  const int nstrip = (p.rows + TI - 1) / TI;
+  const int64_t ntask = (int64_t)ntj * nstrip;
+  const uint32_t ring0 = smem_u32(ring), full0 = smem_u32(bars), empty0 = full0 + 8 * NS;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, CW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc[NBLK][2];
+#pragma unroll
+  for (int b = 0; b < NBLK; ++b) acc[b][0] = acc[b][1] = 0.0;
+
+  if (warp == CW) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      const uint32_t tx = (uint32_t)((8 * NB + 1 + (p.has_e ? 1 : 0)) * PB);
+      for (int64_t task = blockIdx.x; task < ntask; task += gridDim.x) {
+        const int strip = (int)(task / ntj), tj = (int)(task - (int64_t)strip * ntj);
+        const int i0 = strip * TI, i1 = min(i0 + TI, p.rows), j0 = tj * TJ;
+        for (int r = i0 - 1; r <= i1; ++r) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const uint32_t dst = ring0 + s * SB, fb = full0 + 8 * s;
+          mbar_expect_tx(fb, tx);
+          tma_load_3d(dst, &tmV, j0 - 4, r + 2, 0, fb);  // stored row index = grid row + halo (2)
+          tma_load_2d(dst + 8 * NB * PB, &tmY, j0 - 4, r + 2, fb);
+          if (p.has_e) tma_load_2d(dst + 8 * NB * PB + YE, &tmE, j0 - 4, r + 2, fb);
+          if (++s == NS) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // the sign is folded into the weights (exact: every product and every sum is negated symmetrically)
+    const double sg = p.sign;
+    const double d0 = __dadd_rn(4.0 * p.c_lap, -p.c_adv);
+    const double cd = sg * __dadd_rn(-p.c_lap, p.c_adv), cu = sg * -p.c_lap, cl = sg * -p.c_lap;
+    // per column block: byte offset of this lane's pair inside a slot, and what the column is.  Only the LAST block can
+    // hold anything but basis columns (k >= 8 (NB - 1) by the choice of NB).
+    uint32_t poff[NB];
+#pragma unroll
+    for (int I = 0; I < NB; ++I) poff[I] = (uint32_t)((8 * I + g) * PB + 8 * (4 + 8 * warp + 2 * t));
+    const int lastcol = 8 * (NB - 1) + g;
+    const int lastkind = lastcol < p.k ? 0 : (lastcol == p.k ? 1 : 2);  // 0 basis column, 1 the residual, 2 padding
+    if (lastkind == 1) poff[NB - 1] = (uint32_t)(8 * NB * PB + 8 * (4 + 8 * warp + 2 * t));
+    if (lastkind == 2) poff[NB - 1] = poff[0];                          // any valid address; the value is discarded
+    const uint32_t eoff = (uint32_t)(8 * NB * PB + YE + 8 * (4 + 8 * warp + 2 * t));
+    // ring position: slot index and phase advance together (no modulo in the loop)
+    uint32_t slot = 0, phase = 0;
+    auto advance = [&]() {
+      if (++slot == NS) {
+        slot = 0;
+        phase ^= 1u;
+      }
+    };
+    // One grid row: `dn` receives row i + 1 from the ring, then row i (held in `mid`, its slot still resident at
+    // mid_base) is processed with `up` = row i - 1.  Called with the three register rows in rotating roles, so the
+    // window never has to be copied.
+    auto row_step = [&](double2 (&up)[NB], double2 (&mid)[NB], double2 (&dn)[NB], uint32_t& mid_base,
+                        uint32_t& mid_slot, double* const (&jp)[NB], int64_t ro, bool active) {
+      mbar_wait(full0 + 8 * slot, phase);
+      const uint32_t base = ring0 + slot * SB;
+#pragma unroll
+      for (int I = 0; I < NB; ++I) dn[I] = lds2(base + poff[I]);
+      double lf[NB], rt[NB];
+#pragma unroll
+      for (int I = 0; I < NB; ++I) {
+        lf[I] = lds1(mid_base + poff[I] - 8);
+        rt[I] = lds1(mid_base + poff[I] + 16);
+      }
+      double2 e = make_double2(0.0, 0.0);
+      if (p.has_e) e = lds2(mid_base + eoff);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);  // the mid row's slot goes back to the producer
+      mid_base = base;
+      mid_slot = slot;
+      advance();
+      const double dga = sg * __dadd_rn(d0, __dmul_rn(p.lam, e.x)), dgb = sg * __dadd_rn(d0, __dmul_rn(p.lam, e.y));
+      double2 tile[NB];
+#pragma unroll
+      for (int I = 0; I < NB; ++I) {
+        const double oa = apply_refbits(cu, cl, dga, cd, up[I].x, lf[I], mid[I].x, mid[I].y, dn[I].x);
+        const double ob = apply_refbits(cu, cl, dgb, cd, up[I].y, mid[I].x, mid[I].y, rt[I], dn[I].y);
+        tile[I] = make_double2(oa, ob);
+        if (I < NB - 1) {
+          if (active) __stcs(reinterpret_cast<double2*>(jp[I] + ro), tile[I]);
+        } else {
+          if (lastkind == 0) {
+            if (active) __stcs(reinterpret_cast<double2*>(jp[I] + ro), tile[I]);
+          } else if (lastkind == 1) {
+            tile[I] = mid[I];
+          } else {
+            tile[I] = make_double2(0.0, 0.0);
+          }
+        }
+        if (!active) tile[I] = make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int I = 0; I < NB; ++I)
+#pragma unroll
+        for (int J = I; J < NB; ++J) {
+          const int b = blk_index(NB, I, J);
+          dmma(acc[b][0], acc[b][1], tile[I].x, tile[J].x);
+          dmma(acc[b][0], acc[b][1], tile[I].y, tile[J].y);
+        }
+    };
+    for (int64_t task = blockIdx.x; task < ntask; task += gridDim.x) {
+      const int strip = (int)(task / ntj), tj = (int)(task - (int64_t)strip * ntj);
+      const int i0 = strip * TI, i1 = min(i0 + TI, p.rows);
+      const int j = tj * TJ + 8 * warp + 2 * t;
+      const bool active = tj * TJ + 8 * warp < m;  // the last tile of a row may be narrower than TJ (whole segments)
+      double2 ra[NB], rb[NB], rc[NB];
+      {  // row i0 - 1
+        mbar_wait(full0 + 8 * slot, phase);
+        const uint32_t base = ring0 + slot * SB;
+#pragma unroll
+        for (int I = 0; I < NB; ++I) ra[I] = lds2(base + poff[I]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+        advance();
+      }
+      uint32_t mid_base, mid_slot;
+      {  // row i0
+        mbar_wait(full0 + 8 * slot, phase);
+        mid_base = ring0 + slot * SB;
+        mid_slot = slot;
+#pragma unroll
+        for (int I = 0; I < NB; ++I) rb[I] = lds2(mid_base + poff[I]);
+        advance();
+      }
+      double* jp[NB];  // this lane's J V columns at (row 0, j); ro = i * m advances with the rows
+#pragma unroll
+      for (int I = 0; I < NB; ++I) jp[I] = JV + (int64_t)(8 * I + g) * p.ldjv + j;
+      int64_t ro = (int64_t)i0 * m;
+      int i = i0;
+      while (true) {  // three rows per trip, the window rotating through (ra, rb, rc)
+        row_step(ra, rb, rc, mid_base, mid_slot, jp, ro, active);
+        ro += m;
+        if (++i == i1) break;
+        row_step(rb, rc, ra, mid_base, mid_slot, jp, ro, active);
+        ro += m;
+        if (++i == i1) break;
+        row_step(rc, ra, rb, mid_base, mid_slot, jp, ro, active);
+        ro += m;
+        if (++i == i1) break;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);  // row i1 was only ever a dn row
+    }
+  }
+  reduce_gram<NBLK, CW, NT>(acc, red, partials, ticket, Gout);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+// tensor map over stored columns: [ncols][rows + 2 halo][m] doubles, column stride ld; box {pw, 1, ncol_box}
+int make_column_map(CUtensorMap* tm, const double* base, int m, int stored_rows, int64_t ld, int ncols, int ncol_box,
+                    int pw) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  GNK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  CUresult r;
+  if (ncol_box > 1 || ncols > 1) {
+    cuuint64_t dims[3] = {(cuuint64_t)m, (cuuint64_t)stored_rows, (cuuint64_t)ncols};
+    cuuint64_t strides[2] = {(cuuint64_t)m * 8, (cuuint64_t)ld * 8};
+    cuuint32_t box[3] = {(cuuint32_t)pw, 1, (cuuint32_t)ncol_box};
+    cuuint32_t es[3] = {1, 1, 1};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)stored_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)m * 8};
+    cuuint32_t box[2] = {(cuuint32_t)pw, 1};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    gnk_set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return -3;
+  }
+  return 0;
+}
+
+constexpr int SG_CW = 8;  // consumer warps of the fused kernel
+
+template <int NB, int RU>
+int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu, const double* d_V,
+                     int64_t ldv, int v_cols, int k, const double* d_r, double sign, double* d_JV, int64_t ldjv,
+                     double sign_a, double* d_out, cudaStream_t st) {
+  if (int rc = ensure_scratch(ctx, st)) return rc;
+  double* base = ctx->d_cholqr;
+  constexpr int CW = SG_CW;
+  constexpr int PW = 8 * CW + 8, TJ = 8 * CW;
+  const int stored_rows = lay->rows + 2 * lay->halo;
+  CUtensorMap tmV, tmY, tmE;
+  if (int rc = make_column_map(&tmV, d_V, lay->m, stored_rows, ldv, v_cols, 8 * NB, PW)) return rc;
+  if (int rc = make_column_map(&tmY, d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
+  const bool has_e = prm->lam != 0.0;
+  if (int rc = make_column_map(&tmE, has_e ? d_expu : d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
+  auto kern = stencil_gram_kernel<NB, CW>;
+  constexpr int dyn = sg_slot_bytes<NB, CW>() * sg_nslot<NB, CW>();
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    GNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    attr_set[ctx->device & 63] = true;
+  }
+  const int ntj = (lay->m + TJ - 1) / TJ;
+  int TI = 64;
+  while (TI > 8 && (int64_t)ntj * ceil_div(lay->rows, TI) < 6LL * ctx->sm_count) TI >>= 1;
+  const int64_t ntask = (int64_t)ntj * ceil_div(lay->rows, TI);
+  const int ctas = (int)(ntask < ctx->sm_count ? ntask : ctx->sm_count);
+  StencilPanel p{lay->m, lay->rows, k, has_e ? 1 : 0, ldjv, prm->c_lap, prm->c_adv, prm->lam, sign};
+  kern<<<ctas, 32 * (CW + 1), dyn, st>>>(tmV, tmY, tmE, p, TI, d_JV, base + CQ_PART, ctx->d_tickets + TK_CHOLQR,
+                                        base + CQ_LOCAL);
+  GNK_LAUNCH_CHECK(ctx);
+  return cholqr_tail<NB, RU>(ctx, d_JV, ldjv, lay->n_own, k, d_r + lay->off, sign_a, d_out, st);
+}
+
 }  // namespace
 
 // Called by gnk_tsqr_ls (tsqr.cu) for the panels it found eligible (3 <= k+1 <= 32 columns, >= 16384 rows, even row
@@ -751,4 +1105,34 @@ int gnk_cholqr_try(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows,
   if (c <= 24) return run_cholqr<3, 1>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
   if (c <= 32) return run_cholqr<4, 1>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
   return 1;
+}
+
+// gnk_stencil_gram_ls (gnk_b200.h): J V_k written AND the projected least squares solved with the panel read once.
+// Returns 1 when the panel is not eligible for the fused tensor-pipe path (the caller then runs gnk_stencil_apply +
+// gnk_tsqr_ls): the same conditions as gnk_tsqr_ls's tensor-pipe path, plus whole 8-point segments per grid row.
+extern "C" int gnk_stencil_gram_ls(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
+                                   const double* d_V, int64_t ldv, int v_cols, int k, const double* d_r, double sign,
+                                   double* d_JV, int64_t ldjv, double sign_a, double* d_out, void* stream) {
+  GNK_REQUIRE(ctx && lay && prm && d_V && d_r && d_JV && d_out, "gnk_stencil_gram_ls: null argument");
+  GNK_REQUIRE(lay->m > 0 && lay->rows > 0 && lay->halo == 2 && lay->off == 2LL * lay->m &&
+                  lay->n_own == (int64_t)lay->rows * lay->m && lay->ld >= (int64_t)(lay->rows + 4) * lay->m,
+              "gnk_stencil_gram_ls: inconsistent stencil layout");
+  GNK_REQUIRE(k >= 1 && k + 1 <= GNK_MAX_BASIS && v_cols >= k, "gnk_stencil_gram_ls: k out of range");
+  GNK_REQUIRE(prm->lam == 0.0 || d_expu, "gnk_stencil_gram_ls: e^u diagonal required when lam != 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  static const int cholqr_on = getenv("GNK_LS_CHOLQR") ? atoi(getenv("GNK_LS_CHOLQR")) : 1;
+  static const int cholqr_min = getenv("GNK_LS_CHOLQR_MIN") ? atoi(getenv("GNK_LS_CHOLQR_MIN")) : 3;
+  static const int fused_on = getenv("GNK_LS_FUSED") ? atoi(getenv("GNK_LS_FUSED")) : 1;
+  const int c = k + 1;
+  const bool aligned = (lay->m % 8 == 0) && (ldv % 2 == 0) && (ldjv % 2 == 0) && (lay->ld % 2 == 0) &&
+                       ((uintptr_t)d_V % 16 == 0) && ((uintptr_t)d_r % 16 == 0) && ((uintptr_t)d_JV % 16 == 0) &&
+                       (d_expu == nullptr || (uintptr_t)d_expu % 16 == 0);
+  if (!(fused_on && cholqr_on && ctx->ls_method != 1 && (sign == 1.0 || sign == -1.0) &&
+        (sign_a == 1.0 || sign_a == -1.0) && aligned && lay->n_own >= 16384 && c <= 32 && c >= cholqr_min &&
+        encode_tiled_fn() != nullptr))
+    return 1;
+  if (c <= 8) return run_stencil_gram<1, 4>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a, d_out, st);
+  if (c <= 16) return run_stencil_gram<2, 2>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a, d_out, st);
+  if (c <= 24) return run_stencil_gram<3, 1>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a, d_out, st);
+  return run_stencil_gram<4, 1>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a, d_out, st);
 }

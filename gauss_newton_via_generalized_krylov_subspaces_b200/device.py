@@ -162,10 +162,10 @@ class Runtime:
 
 
 class _Mark:
-    __slots__ = ("rt", "name", "nbytes", "e0")
+    __slots__ = ("rt", "name", "nbytes", "e0", "cancel")
 
     def __init__(self, rt, name, nbytes):
-        self.rt, self.name, self.nbytes = rt, name, nbytes
+        self.rt, self.name, self.nbytes, self.cancel = rt, name, nbytes, False
 
     def __enter__(self):
         if self.rt.prof is not None:
@@ -174,7 +174,7 @@ class _Mark:
         return self
 
     def __exit__(self, *exc):
-        if self.rt.prof is not None:
+        if self.rt.prof is not None and not self.cancel:
             e1 = self.rt.torch.cuda.Event(enable_timing=True)
             e1.record()
             self.rt.prof.setdefault(self.name, []).append((self.e0, e1, self.nbytes))

@@ -303,25 +303,8 @@ def gauss_newton_krylow(
 
     JV = None
     jv_cap = 0
-    jv_valid = 0  # leading columns of JV that already hold J_current V (written by gnk_cgs_update_spmm)
-    # GNK_FUSED_DOTS=1: the Gram-Schmidt pass h = V_k^T w also writes J_new V_k for the next outer iteration
-    # (gnk_stencil_apply_dots; the next SpMM shrinks to the appended column).  GNK_FUSED_UPDATE=1 fuses the SpMM into
-    # the *update* pass instead.  Both are correct (J V bit-identical) but measured slower at 4096^2 than the separate
-    # kernels, which already run at 0.95-1.0 of the HBM roofline: k = 30: 2.07 ms (dots) / 2.55 ms (update) against
-    # 1.32 + 0.63 ms; the per-CTA reduction tail / the 8-row register tiles cost more than the saved pass over V_k.
-    # The fused h also differs from gnk_cgs_dots by summation order, which the degenerate linear runs amplify.
-    fuse_mode = None
-    if is_bratu and os.environ.get("GNK_FUSED_UPDATE", "0") == "1":
-        fuse_mode = "update"
-    elif is_bratu and os.environ.get("GNK_FUSED_DOTS", "0") == "1":
-        fuse_mode = "dots"
-    fuse_update = fuse_mode is not None
-    # GNK_FUSED_LS=1 forms J V_k inside the TSQR leaf (saves the n x k buffer and its 16nk bytes of traffic); measured
-    # 14 % slower than SpMM + TSQR at 4096^2 because the leaf is issue-bound, so it is opt-in
-    fuse_ls = is_bratu and os.environ.get("GNK_FUSED_LS", "0") == "1"
     state = {"pending": False}  # pending: the last basis expansion left its breakdown flag unread (see below)
-    defer_ok = (ls_solver == "qr" and not fuse_ls and not fuse_update
-                and os.environ.get("GNK_DEFER_BREAKDOWN", "1") != "0")
+    defer_ok = ls_solver == "qr" and os.environ.get("GNK_DEFER_BREAKDOWN", "1") != "0"
 
     for iter in range(1, max_iter):
         # One host synchronisation per outer iteration: the breakdown flag of the previous basis expansion is not read
@@ -331,26 +314,28 @@ def gauss_newton_krylow(
         for attempt in (0, 1):
             k = krylow.k
             state["rank_reported"] = False
-            # Bratu + QR: J V_k is formed inside the TSQR leaf and never stored (gnk_tsqr_ls_stencil, k <= 31)
-            fused = (fuse_ls and ls_solver == "qr" and k <= 31 and not jac_ev.transposed and jac_ev.scale == 1.0)
-            if not fused and k > jv_cap:
+            if k > jv_cap:
                 jv_cap = min(MAX_COLUMNS, max(krylow.cap, k))
                 JV = rt.empty(jv_cap * ldjv)
-                jv_valid = 0
             # projected operator and projected least squares  (:86-89)
-            if fused:
-                with rt.mark("spmm+tsqr", 8.0 * n_res_own * (k + 2)):
-                    prob.d.tsqr_fused(jac_ev.expu, krylow.V, ld, k, F_cur, -1.0, blk)
-            elif jv_valid >= k:
-                pass  # every column of J V_k was already written by the fused Gram-Schmidt update pass
-            elif jv_valid == k - 1 and k > 1:
-                with rt.mark("spmm", 8.0 * n_res_own * 3):  # only the column appended since
-                    jac_ev.matmat(krylow.col(k - 1), ld, 1, JV[(k - 1) * ldjv:], ldjv)
-            else:
+            ls_done = False
+            # Bratu + QR: one TMA-staged kernel applies the stencil, stores J V_k and forms the Gram matrix of the
+            # panel in the same sweep (gnk_stencil_gram_ls); it answers 1 when the panel does not qualify
+            if (is_bratu and ls_solver == "qr" and ls_method == 0 and not jac_ev.transposed
+                    and jac_ev.scale == 1.0):
+                with rt.mark("spmm+ls", 8.0 * n_res_own * (2 * k + 2)) as mk:
+                    rc = lib.gnk_stencil_gram_ls(rt.ctx, C.byref(sol_lay), C.byref(prob.d.prm), ptr(jac_ev.expu),
+                                                 ptr(krylow.V), ld, krylow.cap, k, ptr(F_cur), -1.0, ptr(JV), ldjv,
+                                                 -1.0, ptr(blk), rt.stream)
+                    mk.cancel = rc != 0
+                if rc == 0:
+                    ls_done = True
+                elif rc != 1:
+                    _lib.check(rc, "gnk_stencil_gram_ls")
+            if not ls_done:
                 with rt.mark("spmm", 8.0 * n_res_own * (2 * k + 1)):
                     jac_ev.matmat(krylow.V, ld, k, JV, ldjv)
-            jv_valid = 0
-            if fused:
+            if ls_done:
                 pass
             elif ls_solver == "qr":
                 with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
@@ -369,7 +354,7 @@ def gauss_newton_krylow(
                 state["vals"] = rt.read(blk, _BLK)
                 if state["pending"] and state["vals"][_SC_FLAG:_SC_FLAG + 1].view(np.int32)[0] != 0:
                     raise _DeferredBreakdown()
-                if ls_solver == "qr" and not fused and ls_refused(state["vals"], k):
+                if ls_solver == "qr" and ls_refused(state["vals"], k):
                     raise _LeastSquaresRefused()
                 if ls_solver == "qr" and not state["rank_reported"]:
                     # the reference prints / raises inside linear_least_squares (:32-35), i.e. before any trial is
@@ -421,26 +406,19 @@ def gauss_newton_krylow(
         jac_ev = prob.jacobian(x_trial, aux=aux[1])  # e^x came out of the accepted trial
         njev += 1
 
-        # the update pass can also write J_new V_k for the next iteration (needs the JV buffer of this iteration)
-        k_before = krylow.k
-        sp = None
-        if (fuse_update and JV is not None and not fuse_ls and krylow.k < krylow.cap and krylow.k + 1 <= jv_cap
-                and not jac_ev.transposed and jac_ev.scale == 1.0):
-            sp = (jac_ev, JV, ldjv, fuse_mode)
-        krylow.spmm_done = False
         # defer the breakdown read-back unless this iteration is the last one or ends with a restart (the message
         # of :127 must appear before either)
         defer = defer_ok and iter + 1 < max_iter and iter % krylow_restart != 0
         dflag = ptr(blk, _SC_FLAG) if defer else None
         try:
             if version == "res_old":
-                krylow.dev_update(jac_ev, F_cur, hx, sp, dflag)
+                krylow.dev_update(jac_ev, F_cur, hx, dflag)
             elif version == "res_new":
-                krylow.dev_update(jac_ev, F_trial, hx, sp, dflag)
+                krylow.dev_update(jac_ev, F_trial, hx, dflag)
             elif version == "jac_old_res_old":
-                krylow.dev_update(jac_ev_old, F_cur, hx, sp, dflag)
+                krylow.dev_update(jac_ev_old, F_cur, hx, dflag)
             elif version == "jac_old_res_new":
-                krylow.dev_update(jac_ev_old, F_trial, hx, sp, dflag)
+                krylow.dev_update(jac_ev_old, F_trial, hx, dflag)
             else:
                 raise ValueError(
                     "Variable version must be in ['res_old','res_new','jac_old_res_old','jac_old_res_new']"
@@ -456,8 +434,6 @@ def gauss_newton_krylow(
                 f"Warning: The genearlized krylow subspace is now identical to the whole parameter space at iteration = {iter}"
             )
 
-        if krylow.spmm_done:
-            jv_valid = k_before
         # the trial becomes the current point
         F_cur, F_trial = F_trial, F_cur
         prev_loss = float(vals[_SC_LOSS])
@@ -467,7 +443,6 @@ def gauss_newton_krylow(
 
         if iter % krylow_restart == 0:  # (:135-136)  x = V c equals the accepted trial point bit for bit
             set_c0(krylow.dev_start(x_trial))
-            jv_valid = 0
 
     if not success:
         print("Warning: The gauss_newton_krylow algorithm reached maximal iteration bound before terminating!")

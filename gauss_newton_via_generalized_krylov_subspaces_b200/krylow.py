@@ -51,7 +51,6 @@ class GeneralizedKrylowSubspace:
         self.reorth_passes = int(reorth_passes)
         self.k = 0
         self.V = None
-        self.spmm_done = False
         self._ready = False
 
     # ---------------------------------------------------------------------------------------------
@@ -103,12 +102,9 @@ class GeneralizedKrylowSubspace:
             _lib.check(rt.lib.gnk_combine(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(c), ptr(d), float(s),
                                           ptr(out), rt.stream), "gnk_combine")
 
-    def dev_update(self, jac_op, r, halo_exchange=None, spmm=None, deferred_flag=None):
+    def dev_update(self, jac_op, r, halo_exchange=None, deferred_flag=None):
         """Expand the basis with -J^T r orthogonalised against V_k (krylow.py:55-73).  Raises the same
-        exceptions as the reference; on Breakdown the basis is left unchanged.  ``spmm=(stencil_jacobian, JV,
-        ldjv, mode)`` lets a Gram-Schmidt pass over V_k also write J V_k for the current k columns: mode "dots" fuses
-        it into the first dot-product pass (gnk_stencil_apply_dots), mode "update" into the last update pass
-        (gnk_cgs_update_spmm); returns True if it did.
+        exceptions as the reference; on Breakdown the basis is left unchanged.
         ``deferred_flag`` (a device pointer to an int32): the breakdown flag of krylow.py:66 is written there and NOT
         read back; the column is appended speculatively and the caller inspects the flag with its next read-back
         (one host synchronisation less per outer iteration) and calls ``retract()`` if it was set."""
@@ -120,47 +116,22 @@ class GeneralizedKrylowSubspace:
         n = self.fields["n_own"]
         with rt.mark("spmv_t", 24.0 * n):
             jac_op.neg_rmatvec(r, self.w)
-        did_spmm = False
-        fuse_dots = spmm is not None and len(spmm) > 3 and spmm[3] == "dots"
         for ipass in range(self.reorth_passes):
-            if fuse_dots and ipass == 0:
-                jn, JV, ldjv = spmm[:3]
-                d = jn.pb.dev
-                with rt.mark("spmm+cgs_dots", 8.0 * n * (2 * self.k + 3)):
-                    _lib.check(lib.gnk_stencil_apply_dots(rt.ctx, C.byref(self.lay), C.byref(d.prm), ptr(jn.expu),
-                                                          ptr(self.V), self.ld, self.k, -1.0, ptr(JV), ldjv,
-                                                          ptr(self.w), ptr(self.h), rt.stream),
-                               "gnk_stencil_apply_dots")
-                did_spmm = True
+            with rt.mark("cgs_dots", 8.0 * n * (self.k + 1)):
+                _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.w),
+                                            ptr(self.h), rt.stream), "gnk_cgs_dots")
+            if not rt.fused_reductions:  # else summed over the ranks inside the kernel (peer mailboxes)
                 rt.allreduce(self.h, self.k, 0)
-            else:
-                with rt.mark("cgs_dots", 8.0 * n * (self.k + 1)):
-                    _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.w),
-                                                ptr(self.h), rt.stream), "gnk_cgs_dots")
-                if not rt.fused_reductions:  # else summed over the ranks inside the kernel (peer mailboxes)
-                    rt.allreduce(self.h, self.k, 0)
-            if spmm is not None and not fuse_dots and ipass == self.reorth_passes - 1:
-                jn, JV, ldjv = spmm[:3]
-                d = jn.pb.dev
-                with rt.mark("cgs_update+spmm", 8.0 * n * (2 * self.k + 3)):
-                    _lib.check(lib.gnk_cgs_update_spmm(rt.ctx, C.byref(self.lay), C.byref(d.prm), ptr(jn.expu),
-                                                       ptr(self.V), self.k, ptr(self.h), ptr(self.w), ptr(self.stats),
-                                                       -1.0, ptr(JV), ldjv, rt.stream), "gnk_cgs_update_spmm")
-                did_spmm = True
-                stats_reduced = False
-            else:
-                with rt.mark("cgs_update", 8.0 * n * (self.k + 2)):
-                    _lib.check(lib.gnk_cgs_update(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.h),
-                                                  ptr(self.w), ptr(self.stats), rt.stream), "gnk_cgs_update")
-                stats_reduced = rt.fused_reductions
-        if not stats_reduced:
+            with rt.mark("cgs_update", 8.0 * n * (self.k + 2)):
+                _lib.check(lib.gnk_cgs_update(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(self.h),
+                                              ptr(self.w), ptr(self.stats), rt.stream), "gnk_cgs_update")
+        if not rt.fused_reductions:
             rt.allreduce(self.stats, 2, 2)
         new = self.col(self.k)
         with rt.mark("normalize", 16.0 * n):
             _lib.check(lib.gnk_normalize(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8, ptr(new),
                                          ptr(self.flag) if deferred_flag is None else deferred_flag, rt.stream),
                        "gnk_normalize")
-        self.spmm_done = did_spmm
         if deferred_flag is None and int(rt.read_i32(self.flag)[0]) != 0:
             raise GeneralizedKrylowSubspaceBreakdown(
                 "Normal residual is allready inside generalized Krylow Subspcae, there for gauss newton krylow "
@@ -168,7 +139,6 @@ class GeneralizedKrylowSubspace:
         if halo_exchange is not None:
             halo_exchange(self.V, 2, self.k * self.ld)
         self.k += 1
-        return did_spmm
 
     def retract(self):
         """undo a speculative append whose deferred breakdown flag turned out to be set (the column was not written)"""

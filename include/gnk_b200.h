@@ -108,24 +108,6 @@ int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, 
 int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_h,
                    double* d_w, double* d_stats, void* stream);
 
-/* gnk_cgs_dots fused with the NEXT outer iteration's gnk_stencil_apply: one pass over V_k writes
- * JV[:, j] = sign * (M V[:, j]) (Jacobian given by d_expu: the new one, gauss_newton_krylow.py:107 precedes the basis
- * update :110-118) and h[j] = V[:, j] . w over the owned rows (krylow.py:64, first half), j < k.  Saves one of the six
- * passes over V_k per outer iteration.  J V is bit-identical to gnk_stencil_apply; h differs from gnk_cgs_dots by
- * summation order only.  d_w is a stored column, JV columns hold the owned rows (stride ldjv). */
-int gnk_stencil_apply_dots(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
-                           const double* d_V, int64_t ldv, int k, double sign, double* d_JV, int64_t ldjv,
-                           const double* d_w, double* d_h, void* stream);
-
-/* gnk_cgs_update fused with the NEXT outer iteration's gnk_stencil_apply: in the one pass over V_k that forms
- * w -= V_k h it also writes JV[:, j] = sign * (M V[:, j]) for j < k with the Jacobian given by d_expu (the new one:
- * gauss_newton_krylow.py:107 precedes the basis update :110-118), saving the re-read of V_k by the SpMM of
- * gauss_newton_krylow.py:86.  Same arithmetic, bit for bit, as the two separate kernels.  JV columns hold the owned
- * rows only (stride ldjv). */
-int gnk_cgs_update_spmm(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
-                        const double* d_V, int k, const double* d_h, double* d_w, double* d_stats, double sign,
-                        double* d_JV, int64_t ldjv, void* stream);
-
 /* ---- projected least squares (gauss_newton_krylow.py:16-36, :89) ------------------------------- */
 /* Householder TSQR of the n_rows x (k+1) panel [sign_a*A | y] (A column-major, stride lda) and
  * solution of min || sign_a*A d - y ||_2.  Results (device): d_out[0..k) = d, d_out[k] = ||R d||^2
@@ -144,19 +126,26 @@ int gnk_cgs_update_spmm(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* pr
 int gnk_tsqr_ls(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k,
                 const double* d_y, double sign_a, double* d_out, void* stream);
 
+/* Projected operator AND projected least squares of one GNK outer iteration in one call, for the Bratu stencil
+ * (gauss_newton_krylow.py:86 `JV = jac_ev @ krylow.basis` followed by :89 `linear_least_squares(-1 * JV, res_ev)`):
+ *   JV[:, j] = sign * (M V[:, j]), j < k   -- written (owned rows, column stride ldjv), bit-identical to gnk_stencil_apply
+ *   d_out    = the result block of gnk_tsqr_ls(JV, ldjv, n_own, k, r, sign_a)
+ * with the least-squares panel READ ONCE: a TMA-staged, warp-specialised kernel streams V_k through shared memory
+ * (cp.async.bulk.tensor row slots, mbarrier ring), applies the stencil, stores J V and accumulates the Gram matrix of
+ * [J V | r] with FP64 tensor-core MMAs in the same sweep; the refinement (or second CholeskyQR2) pass then reads J V
+ * once more.  d_V: v_cols >= k stored columns (stride ldv, halo rows valid), d_r: the residual as a stored column,
+ * d_expu as in gnk_stencil_apply.  Returns 1 -- nothing launched -- when the panel does not qualify (fewer than 16384
+ * owned unknowns, more than 32 panel columns, m not a multiple of 8, Householder path pinned, GNK_LS_FUSED=0, ...): the
+ * caller then issues gnk_stencil_apply + gnk_tsqr_ls.  Refusal (d_out[k+2] = -1) as for gnk_tsqr_ls; J V is valid then. */
+int gnk_stencil_gram_ls(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
+                        const double* d_V, int64_t ldv, int v_cols, int k, const double* d_r, double sign,
+                        double* d_JV, int64_t ldjv, double sign_a, double* d_out, void* stream);
+
 /* Factorisation used by gnk_tsqr_ls: 0 = automatic (tensor-pipe path where eligible, Householder TSQR otherwise; the
  * default -- GNK_LS_CHOLQR=0 in the environment disables the tensor-pipe path), 1 = Householder TSQR only,
  * 2 = as 0 but always the second CholeskyQR2 pass, never the refinement form.  Returns the previous setting, or a
  * negative status. */
 int gnk_tsqr_ls_method(gnk_ctx* ctx, int method);
-
-/* Fused form of gnk_stencil_apply + gnk_tsqr_ls for the Bratu stencil: the panel [sign_a * (J V_k) | r] is formed on
- * the fly from the basis columns inside the TSQR leaf (tiles are 8 x 32 blocks of the grid staged with a one-cell
- * halo), so J V_k (gauss_newton_krylow.py:86) is never written to or re-read from HBM.  d_V: k stored columns
- * (stride ldv, halo rows valid); d_r: the residual as a stored column; d_out as gnk_tsqr_ls.  k <= 31. */
-int gnk_tsqr_ls_stencil(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
-                        const double* d_V, int64_t ldv, int k, const double* d_r, double sign_a,
-                        double* d_out, void* stream);
 
 /* ---- generic sparse Jacobians (rosenbrock_problem.py:14-19, foreign callables) ----------------- */
 /* out[:, j] = sign * A * in[:, j] for a CSR matrix with n_rows rows; in columns start at

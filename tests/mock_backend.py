@@ -179,15 +179,6 @@ class MockLib:
             s[1] = np.max(np.abs(wv)) if wv.size else 0.0
         return 0
 
-    def gnk_stencil_apply_dots(self, ctx, lay, prm, expu, V, ldv, k, sign, JV, ldjv, w, h, stream):
-        self.gnk_stencil_apply(ctx, lay, prm, expu, V, ldv, k, sign, 0, JV, ldjv, 0, stream)
-        return self.gnk_cgs_dots(ctx, lay, V, k, w, h, stream)
-
-    def gnk_cgs_update_spmm(self, ctx, lay, prm, expu, V, k, h, w, stats, sign, JV, ldjv, stream):
-        lay_o = obj(lay)
-        self.gnk_stencil_apply(ctx, lay, prm, expu, V, lay_o.ld, k, sign, 0, JV, ldjv, 0, stream)
-        return self.gnk_cgs_update(ctx, lay, V, k, h, w, stats, stream)
-
     # ---- least squares: per-rank QR, gather of R factors, QR of the stack (the TSQR tree) ----
     def gnk_tsqr_ls(self, ctx, A, lda, n_rows, k, y, sign_a, out, stream):
         self.launches += 1
@@ -218,16 +209,6 @@ class MockLib:
         self.ls_method = int(method)
         return prev
 
-    def gnk_tsqr_ls_stencil(self, ctx, lay, prm, expu, V, ldv, k, r, sign_a, out, stream):
-        lay_o = obj(lay)
-        n = lay_o.n_own
-        JV = np.zeros(k * n)
-        self.gnk_stencil_apply(ctx, lay, prm, expu, V, ldv, k, -1.0, 0, C.c_void_p(JV.ctypes.data), n, 0, stream)
-        rv = arr(r, lay_o.ld)[lay_o.off:lay_o.off + n].copy()
-        return self.gnk_tsqr_ls(ctx, C.c_void_p(JV.ctypes.data), n, n, k, C.c_void_p(rv.ctypes.data), sign_a, out,
-                                stream)
-
-    # ---- CSR ----
     def gnk_spmm_csr(self, ctx, n_rows, rowptr, col, val, inp, in_ld, in_off, k, sign, out, out_ld, out_off, stream):
         import scipy.sparse as sp
         self.launches += 1
@@ -293,6 +274,9 @@ class MockLib:
         self.launches += 1
         arr(out, 1)[0] = np.dot(arr(x, n), arr(y, n))
         return 0
+
+    def gnk_stencil_gram_ls(self, *a):
+        return 1  # "not eligible": the host falls back to gnk_stencil_apply + gnk_tsqr_ls (which the mock implements)
 
     # ---- CGLS (scipy cg restated; single rank) ----
     def gnk_cgls(self, ctx, op, y, rtol, preconditioner, x, work, iters, stream):

@@ -488,116 +488,76 @@ def test_armijo_goldstein_public_api(g):
         g.armijo_goldstein(res, x, r, J, (5,), -d)
 
 
-@pytest.mark.parametrize("G,k", [(12, 1), (12, 5), (35, 8), (34, 15), (130, 7), (131, 20), (258, 31), (1030, 12)])
-def test_fused_stencil_tsqr_matches_unfused(g, G, k):
-    """gnk_tsqr_ls_stencil (J V_k formed inside the TSQR leaf) against gnk_stencil_apply + gnk_tsqr_ls."""
+@pytest.mark.parametrize("G,k,lam", [(129, 2, 10.0), (129, 7, 10.0), (137, 8, 10.0), (201, 15, 10.0), (257, 16, 3.0),
+                                      (265, 23, 10.0), (513, 24, 10.0), (521, 31, 10.0), (1025, 30, 10.0),
+                                      (193, 12, 0.0)])
+def test_stencil_gram_ls_matches_apply_plus_tsqr(g, G, k, lam):
+    """gnk_stencil_gram_ls (TMA-staged kernel: stencil + J V store + Gram matrix in one sweep, then the refinement
+    pass) against gnk_stencil_apply + gnk_tsqr_ls: J V bit-identical, the result block equal to rounding (the two Gram
+    matrices are summed in different orders), d against numpy's lstsq.  Covers 1..4 column blocks, rows that are not a
+    multiple of the strip height, row lengths that are multiples of 8 but not of the 64-point tile (partial tiles,
+    idle consumer warps), lam = 0 (no e^u plane)."""
     _lib, device = _lib_mods()
     from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve
-    pb = g.BratuPdeProblem(G, 5, 10)
+    pb = g.BratuPdeProblem(G, 5, lam)
     d = pb.dev
-    rt = d.rt
+    rt, lib = d.rt, d.rt.lib
     n, ld, off = d.fields["n_own"], d.ld, d.fields["off"]
+    assert pb.m % 8 == 0 and n >= 16384
     rs = np.random.RandomState(G * 100 + k)
-    V = rt.zeros(k * ld)
-    for j in range(k):
+    cap = k + 3
+    V = rt.zeros(cap * ld)
+    for j in range(cap):  # columns beyond k hold data too: they must not leak into the panel
         d.upload_x(rs.normal(size=pb.n), V[j * ld:(j + 1) * ld])
     u, r = d.new_col(), d.new_col()
     d.upload_x(0.3 * rs.normal(size=pb.n), u)
     d.upload_x(rs.normal(size=pb.n), r)
-    E = d.new_col()
-    d.residual_into(u, d.zero_col(), d.new_col(), E, d.scal_tmp, depth=0)
+    E = None
+    if lam != 0:
+        E = d.new_col()
+        d.residual_into(u, d.zero_col(), d.new_col(), E, d.scal_tmp, depth=0)
     ldjv = (n + 15) // 16 * 16
-    JV = rt.zeros(k * ldjv)
-    d.apply(E, V, ld, k, -1.0, 0, JV, ldjv, 0)
+    JVa, JVb = rt.zeros(k * ldjv), rt.zeros(k * ldjv)
+    d.apply(E, V, ld, k, -1.0, 0, JVa, ldjv, 0)
     a, b = rt.zeros(256), rt.zeros(256)
-    tsqr_solve(rt, JV, ldjv, n, k, r[off:], -1.0, a)
-    d.tsqr_fused(E, V, ld, k, r, -1.0, b)
+    tsqr_solve(rt, JVa, ldjv, n, k, r[off:], -1.0, a)
+    rc = lib.gnk_stencil_gram_ls(rt.ctx, C.byref(d.lay), C.byref(d.prm), device.ptr(E), device.ptr(V), ld, cap, k,
+                                 device.ptr(r), -1.0, device.ptr(JVb), ldjv, -1.0, device.ptr(b), rt.stream)
+    assert rc == 0, rc
     va, vb = rt.read(a, 2 * k + 4), rt.read(b, 2 * k + 4)
-    JVh = rt.download(JV).reshape(k, ldjv)[:, :n].T
+    assert np.array_equal(rt.download(JVa), rt.download(JVb)), "J V differs from gnk_stencil_apply"
+    JVh = rt.download(JVa).reshape(k, ldjv)[:, :n].T
     dref = np.linalg.lstsq(-JVh, rt.download(r[off:off + n]), rcond=None)[0]
     cond = np.linalg.cond(JVh)
-    assert rel(vb[:k], dref) < 1e-13 * max(cond, 10.0) and rel(va[:k], dref) < 1e-13 * max(cond, 10.0)
-    assert np.allclose(vb[k:k + 4], va[k:k + 4], rtol=1e-11, atol=0)           # |Rd|^2, resid^2, ndef, |d|^2
+    assert vb[k + 2] == 0 and va[k + 2] == 0
+    assert rel(vb[:k], dref) < 1e-13 * max(cond, 10.0) and rel(vb[:k], va[:k]) < 1e-13 * max(cond, 10.0)
+    assert np.allclose(vb[k:k + 4], va[k:k + 4], rtol=1e-9, atol=0)            # |A d0|^2, resid^2, ndef, |d|^2
     assert np.allclose(np.abs(vb[k + 4:]), np.abs(va[k + 4:]), rtol=1e-11)       # |diag R|
+    # run-to-run deterministic
+    b2 = rt.zeros(256)
+    lib.gnk_stencil_gram_ls(rt.ctx, C.byref(d.lay), C.byref(d.prm), device.ptr(E), device.ptr(V), ld, cap, k,
+                            device.ptr(r), -1.0, device.ptr(JVb), ldjv, -1.0, device.ptr(b2), rt.stream)
+    assert np.array_equal(rt.read(b2, 2 * k + 4), vb)
 
 
-@pytest.mark.parametrize("G,k", [(12, 1), (13, 5), (35, 8), (130, 7), (131, 20), (258, 30), (1030, 12)])
-def test_fused_update_spmm_matches_separate_kernels(g, G, k):
-    """gnk_cgs_update_spmm (Gram-Schmidt update that also writes J V_k) is bit-for-bit gnk_cgs_update + gnk_stencil_apply."""
+def test_stencil_gram_ls_declines_ineligible_panels(g):
+    """panels the fused tensor-pipe path does not take are answered with 1 and nothing is launched: small slabs, row
+    lengths that are not a multiple of 8, more than 32 panel columns, the Householder path pinned"""
     _lib, device = _lib_mods()
-    pb = g.BratuPdeProblem(G, 5, 10)
-    d = pb.dev
-    rt = d.rt
-    lib = rt.lib
-    n, ld, off = d.fields["n_own"], d.ld, d.fields["off"]
-    rs = np.random.RandomState(G * 100 + k)
-    V = rt.zeros(k * ld)
-    for j in range(k):
-        d.upload_x(rs.normal(size=pb.n), V[j * ld:(j + 1) * ld])
-    u, E = d.new_col(), d.new_col()
-    d.upload_x(0.3 * rs.normal(size=pb.n), u)
-    d.residual_into(u, d.zero_col(), d.new_col(), E, d.scal_tmp, depth=0)
-    wh = rs.normal(size=pb.n)
-    w1, w2 = d.new_col(), d.new_col()
-    d.upload_x(wh, w1)
-    d.upload_x(wh, w2)
-    h = rt.zeros(128)
-    rt.upload(rs.normal(size=k), h[:k])
-    ldjv = (n + 15) // 16 * 16
-    JV1, JV2 = rt.zeros(k * ldjv), rt.zeros(k * ldjv)
-    s1, s2 = rt.zeros(2), rt.zeros(2)
-    d.apply(E, V, ld, k, -1.0, 0, JV1, ldjv, 0)
-    _lib.check(lib.gnk_cgs_update(rt.ctx, C.byref(d.lay), device.ptr(V), k, device.ptr(h), device.ptr(w1),
-                                  device.ptr(s1), rt.stream))
-    _lib.check(lib.gnk_cgs_update_spmm(rt.ctx, C.byref(d.lay), C.byref(d.prm), device.ptr(E), device.ptr(V), k,
-                                       device.ptr(h), device.ptr(w2), device.ptr(s2), -1.0, device.ptr(JV2), ldjv,
-                                       rt.stream))
-    a = rt.download(JV1).reshape(k, ldjv)[:, :n]
-    b = rt.download(JV2).reshape(k, ldjv)[:, :n]
-    assert np.array_equal(a, b)
-    wa, wb = rt.download(w1[off:off + n]), rt.download(w2[off:off + n])
-    assert rel(wb, wa) < 1e-14          # same products, accumulated over the columns in the same order
-    ra, rb = rt.read(s1, 2), rt.read(s2, 2)
-    assert abs(ra[0] - rb[0]) <= 1e-12 * ra[0] and abs(ra[1] - rb[1]) <= 1e-14 * ra[1]
-
-
-@pytest.mark.parametrize("G,k", [(12, 1), (13, 5), (35, 8), (130, 7), (131, 20), (258, 30), (1030, 12)])
-def test_fused_spmm_dots_matches_separate_kernels(g, G, k):
-    """gnk_stencil_apply_dots: J V_k bit-for-bit gnk_stencil_apply, h = V_k^T w equal to gnk_cgs_dots up to summation order."""
-    _lib, device = _lib_mods()
-    pb = g.BratuPdeProblem(G, 5, 10)
-    d = pb.dev
-    rt = d.rt
-    lib = rt.lib
-    n, ld, off = d.fields["n_own"], d.ld, d.fields["off"]
-    rs = np.random.RandomState(G * 100 + k)
-    Vh = rs.normal(size=(k, pb.n))
-    V = rt.zeros(k * ld)
-    for j in range(k):
-        d.upload_x(Vh[j], V[j * ld:(j + 1) * ld])
-    u, E, w = d.new_col(), d.new_col(), d.new_col()
-    d.upload_x(0.3 * rs.normal(size=pb.n), u)
-    d.residual_into(u, d.zero_col(), d.new_col(), E, d.scal_tmp, depth=0)
-    wh = rs.normal(size=pb.n)
-    d.upload_x(wh, w)
-    ldjv = (n + 15) // 16 * 16
-    JV1, JV2 = rt.zeros(k * ldjv), rt.zeros(k * ldjv)
-    h1, h2 = rt.zeros(128), rt.zeros(128)
-    d.apply(E, V, ld, k, -1.0, 0, JV1, ldjv, 0)
-    _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(d.lay), device.ptr(V), k, device.ptr(w), device.ptr(h1), rt.stream))
-    outs = []
-    for _ in range(2):  # twice: the self-resetting ticket and the run-to-run determinism of the reduction
-        _lib.check(lib.gnk_stencil_apply_dots(rt.ctx, C.byref(d.lay), C.byref(d.prm), device.ptr(E), device.ptr(V), ld,
-                                              k, -1.0, device.ptr(JV2), ldjv, device.ptr(w), device.ptr(h2),
-                                              rt.stream))
-        outs.append(rt.read(h2, k))
-    assert np.array_equal(outs[0], outs[1])
-    a = rt.download(JV1).reshape(k, ldjv)[:, :n]
-    b = rt.download(JV2).reshape(k, ldjv)[:, :n]
-    assert np.array_equal(a, b)
-    href = Vh @ wh
-    scale = np.linalg.norm(Vh, axis=1) * np.linalg.norm(wh)
-    assert np.all(np.abs(outs[0] - href) <= 1e-14 * scale) and np.all(np.abs(rt.read(h1, k) - href) <= 1e-14 * scale)
+    for G, k, pin in ((101, 5, 0), (134, 5, 0), (257, 40, 0), (257, 5, 1)):
+        pb = g.BratuPdeProblem(G, 5, 10)
+        d = pb.dev
+        rt, lib = d.rt, d.rt.lib
+        n, ld = d.fields["n_own"], d.ld
+        V, r, E = rt.zeros(k * ld), d.new_col(), d.new_col()
+        ldjv = (n + 15) // 16 * 16
+        JV, out = rt.zeros(k * ldjv), rt.zeros(256)
+        prev = lib.gnk_tsqr_ls_method(rt.ctx, pin)
+        l0 = rt.launches()
+        rc = lib.gnk_stencil_gram_ls(rt.ctx, C.byref(d.lay), C.byref(d.prm), device.ptr(E), device.ptr(V), ld, k, k,
+                                     device.ptr(r), -1.0, device.ptr(JV), ldjv, -1.0, device.ptr(out), rt.stream)
+        lib.gnk_tsqr_ls_method(rt.ctx, prev)
+        assert rc == 1 and rt.launches() == l0, (G, k, pin, rc)
 
 
 def test_tsqr_degenerate_inputs(g, capsys):

@@ -109,14 +109,11 @@ def main():
         if want("cgs_update"):
             report("cgs_update", k, timeit(lambda: lib.gnk_cgs_update(rt.ctx, lay, ptr(V), k, ptr(h), ptr(w), ptr(st),
                                                                       rt.stream)), 8.0 * n * (k + 2))
-        if want("spmm_dots"):
-            report("spmm_dots", k, timeit(lambda: lib.gnk_stencil_apply_dots(
-                rt.ctx, lay, prm, ptr(E), ptr(V), ld, k, -1.0, ptr(JV), n, ptr(w), ptr(h), rt.stream)),
-                8.0 * n * (2 * k + 2))
-        if want("update_spmm"):
-            report("update_spmm", k, timeit(lambda: lib.gnk_cgs_update_spmm(
-                rt.ctx, lay, prm, ptr(E), ptr(V), k, ptr(h), ptr(w), ptr(st), -1.0, ptr(JV), n, rt.stream)),
-                8.0 * n * (2 * k + 3))
+        if want("spmm_ls") and k + 1 <= 32:
+            F_col = F
+            report("spmm_ls", k, timeit(lambda: lib.gnk_stencil_gram_ls(
+                rt.ctx, lay, prm, ptr(E), ptr(V), ld, kmax, k, ptr(F_col), -1.0, ptr(JV), n, -1.0, ptr(blk),
+                rt.stream)), 8.0 * n * (2 * k + 2))
     if a.out:
         os.makedirs(os.path.dirname(a.out), exist_ok=True)
         json.dump(dict(m=a.m, n=n, peak_gbs=peak, rows=rows), open(a.out, "w"), indent=1)
