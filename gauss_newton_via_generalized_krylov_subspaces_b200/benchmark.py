@@ -8,12 +8,18 @@ from .armijo_goldstein import StepLengthConvergenceError
 
 
 def ref_method(res, x0, jac, args, callback, **kwargs):
+    """the comparison curve of the reference (benchmark.py:7-11): scipy.optimize.least_squares, a host algorithm.  A
+    device-native Jacobian (the matrix-free stencil operator) is handed to scipy as the assembled CSR matrix."""
     import scipy.optimize
 
     def cb_scipy(intermediate_result):
         callback(intermediate_result.x, intermediate_result.nfev, None)
 
-    scipy.optimize.least_squares(res, x0, jac, callback=cb_scipy, args=args)
+    def jac_host(x, *a):
+        J = jac(x, *a)
+        return J.tocsr() if hasattr(J, "_gnk_sparse_like") else J
+
+    scipy.optimize.least_squares(res, x0, jac_host, callback=cb_scipy, args=args)
 
 
 def reverse_accumulation(nfev_list: List[int]) -> List[int]:

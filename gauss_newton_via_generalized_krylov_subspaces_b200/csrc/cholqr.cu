@@ -789,8 +789,17 @@ template <int CW> __host__ __device__ constexpr int sg_ye_bytes() { return (sg_p
 template <int NB, int CW> __host__ __device__ constexpr int sg_slot_bytes() {
   return 8 * NB * sg_plane_bytes<CW>() + 2 * sg_ye_bytes<CW>();
 }
+// J V leaves through shared memory too: every consumer warp stages its 8-point x 8 NB-column piece of a grid row
+// ([column][8 points], 64 bytes per column) in one of two private buffers and hands it to the TMA unit
+// (cp.async.bulk.tensor store); columns >= k and points >= m are clipped by the tensor map.
+template <int NB> __host__ __device__ constexpr int sg_out_bytes() { return 8 * NB * 64; }
 template <int NB, int CW> __host__ __device__ constexpr int sg_nslot() {
-  return (200 * 1024 / sg_slot_bytes<NB, CW>()) < 16 ? (200 * 1024 / sg_slot_bytes<NB, CW>()) : 16;
+  return ((200 * 1024 - 2 * CW * sg_out_bytes<NB>()) / sg_slot_bytes<NB, CW>()) < 16
+             ? ((200 * 1024 - 2 * CW * sg_out_bytes<NB>()) / sg_slot_bytes<NB, CW>())
+             : 16;
+}
+template <int NB, int CW> __host__ __device__ constexpr int sg_dyn_bytes() {
+  return sg_slot_bytes<NB, CW>() * sg_nslot<NB, CW>() + 2 * CW * sg_out_bytes<NB>();
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -825,6 +834,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                "l"(tm), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0),
+               "r"(c1), "r"(c2), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void sts2(uint32_t a, double2 v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
 __device__ __forceinline__ double2 lds2(uint32_t a) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
@@ -839,8 +856,8 @@ __device__ __forceinline__ double lds1(uint32_t a) {
 template <int NB, int CW>
 __global__ void __launch_bounds__(32 * (CW + 1), 1)
     stencil_gram_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmY,
-                        const __grid_constant__ CUtensorMap tmE, StencilPanel p, int TI, double* __restrict__ JV,
-                        double* __restrict__ partials, unsigned int* ticket, double* __restrict__ Gout) {
+                        const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmJ, StencilPanel p,
+                        int TI, double* __restrict__ partials, unsigned int* ticket, double* __restrict__ Gout) {
   constexpr int NBLK = nblocks(NB);
   constexpr int SB = sg_slot_bytes<NB, CW>();
   constexpr int NS = sg_nslot<NB, CW>();
@@ -903,8 +920,17 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
     const int lastcol = 8 * (NB - 1) + g;
     const int lastkind = lastcol < p.k ? 0 : (lastcol == p.k ? 1 : 2);  // 0 basis column, 1 the residual, 2 padding
     if (lastkind == 1) poff[NB - 1] = (uint32_t)(8 * NB * PB + 8 * (4 + 8 * warp + 2 * t));
-    if (lastkind == 2) poff[NB - 1] = poff[0];                          // any valid address; the value is discarded
+    if (lastkind == 2) poff[NB - 1] = poff[0];                          // any valid (finite) data; multiplied by 0
+    // No selects in the loop: the last block runs the same stencil code with per-lane weights -- a basis column keeps
+    // (cu, cl, dg, cd); the residual column uses (0, 0, 1, 0), which returns `mid` exactly (0 * finite = 0, 0 + x = x);
+    // a padding column uses all zeros.  dg = wsel * (d0 + lam e) + wone is exact for wsel, wone in {0, 1}.
+    const double wsel = lastkind == 0 ? 1.0 : 0.0, wone = lastkind == 1 ? 1.0 : 0.0;
+    const double cuL = wsel * cu, clL = wsel * cl, cdL = wsel * cd;
     const uint32_t eoff = (uint32_t)(8 * NB * PB + YE + 8 * (4 + 8 * warp + 2 * t));
+    // this warp's two output staging buffers and this lane's place in them: column 8 I + g, points 2t, 2t + 1
+    const uint32_t out0 = ring0 + NS * SB + (uint32_t)(2 * warp) * sg_out_bytes<NB>();
+    const uint32_t olane = (uint32_t)(g * 64 + t * 16);
+    uint32_t obuf = 0;
     // ring position: slot index and phase advance together (no modulo in the loop)
     uint32_t slot = 0, phase = 0;
     auto advance = [&]() {
@@ -916,8 +942,16 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
     // One grid row: `dn` receives row i + 1 from the ring, then row i (held in `mid`, its slot still resident at
     // mid_base) is processed with `up` = row i - 1.  Called with the three register rows in rotating roles, so the
     // window never has to be copied.
+    // a warp whose segment lies beyond the row end (last tile of a row, m not a multiple of TJ) only keeps the ring moving
+    auto row_skip = [&](uint32_t& mid_slot) {
+      mbar_wait(full0 + 8 * slot, phase);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);
+      mid_slot = slot;
+      advance();
+    };
     auto row_step = [&](double2 (&up)[NB], double2 (&mid)[NB], double2 (&dn)[NB], uint32_t& mid_base,
-                        uint32_t& mid_slot, double* const (&jp)[NB], int64_t ro, bool active) {
+                        uint32_t& mid_slot, int jseg, int i) {
       mbar_wait(full0 + 8 * slot, phase);
       const uint32_t base = ring0 + slot * SB;
 #pragma unroll
@@ -936,25 +970,29 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
       mid_slot = slot;
       advance();
       const double dga = sg * __dadd_rn(d0, __dmul_rn(p.lam, e.x)), dgb = sg * __dadd_rn(d0, __dmul_rn(p.lam, e.y));
+      // the staging buffer about to be overwritten was handed to the TMA unit two rows ago: its read must be over
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      const uint32_t ob0 = out0 + obuf * sg_out_bytes<NB>();
+      const double dgaL = fma(wsel, dga, wone), dgbL = fma(wsel, dgb, wone);
       double2 tile[NB];
 #pragma unroll
       for (int I = 0; I < NB; ++I) {
-        const double oa = apply_refbits(cu, cl, dga, cd, up[I].x, lf[I], mid[I].x, mid[I].y, dn[I].x);
-        const double ob = apply_refbits(cu, cl, dgb, cd, up[I].y, mid[I].x, mid[I].y, rt[I], dn[I].y);
+        const bool last = I == NB - 1;
+        const double oa = apply_refbits(last ? cuL : cu, last ? clL : cl, last ? dgaL : dga, last ? cdL : cd, up[I].x,
+                                        lf[I], mid[I].x, mid[I].y, dn[I].x);
+        const double ob = apply_refbits(last ? cuL : cu, last ? clL : cl, last ? dgbL : dgb, last ? cdL : cd, up[I].y,
+                                        mid[I].x, mid[I].y, rt[I], dn[I].y);
         tile[I] = make_double2(oa, ob);
-        if (I < NB - 1) {
-          if (active) __stcs(reinterpret_cast<double2*>(jp[I] + ro), tile[I]);
-        } else {
-          if (lastkind == 0) {
-            if (active) __stcs(reinterpret_cast<double2*>(jp[I] + ro), tile[I]);
-          } else if (lastkind == 1) {
-            tile[I] = mid[I];
-          } else {
-            tile[I] = make_double2(0.0, 0.0);
-          }
-        }
-        if (!active) tile[I] = make_double2(0.0, 0.0);
+        sts2(ob0 + I * 512 + olane, tile[I]);  // columns >= k are clipped by the store's tensor map
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmJ, jseg, i, 0, ob0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      obuf ^= 1u;
 #pragma unroll
       for (int I = 0; I < NB; ++I)
 #pragma unroll
@@ -967,7 +1005,6 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
     for (int64_t task = blockIdx.x; task < ntask; task += gridDim.x) {
       const int strip = (int)(task / ntj), tj = (int)(task - (int64_t)strip * ntj);
       const int i0 = strip * TI, i1 = min(i0 + TI, p.rows);
-      const int j = tj * TJ + 8 * warp + 2 * t;
       const bool active = tj * TJ + 8 * warp < m;  // the last tile of a row may be narrower than TJ (whole segments)
       double2 ra[NB], rb[NB], rc[NB];
       {  // row i0 - 1
@@ -988,25 +1025,26 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
         for (int I = 0; I < NB; ++I) rb[I] = lds2(mid_base + poff[I]);
         advance();
       }
-      double* jp[NB];  // this lane's J V columns at (row 0, j); ro = i * m advances with the rows
-#pragma unroll
-      for (int I = 0; I < NB; ++I) jp[I] = JV + (int64_t)(8 * I + g) * p.ldjv + j;
-      int64_t ro = (int64_t)i0 * m;
+      const int jseg = tj * TJ + 8 * warp;  // first grid point of this warp's segment
       int i = i0;
-      while (true) {  // three rows per trip, the window rotating through (ra, rb, rc)
-        row_step(ra, rb, rc, mid_base, mid_slot, jp, ro, active);
-        ro += m;
-        if (++i == i1) break;
-        row_step(rb, rc, ra, mid_base, mid_slot, jp, ro, active);
-        ro += m;
-        if (++i == i1) break;
-        row_step(rc, ra, rb, mid_base, mid_slot, jp, ro, active);
-        ro += m;
-        if (++i == i1) break;
+      if (active) {
+        while (true) {  // three rows per trip, the window rotating through (ra, rb, rc)
+          row_step(ra, rb, rc, mid_base, mid_slot, jseg, i);
+          if (++i == i1) break;
+          row_step(rb, rc, ra, mid_base, mid_slot, jseg, i);
+          if (++i == i1) break;
+          row_step(rc, ra, rb, mid_base, mid_slot, jseg, i);
+          if (++i == i1) break;
+        }
+      } else {
+        for (; i < i1; ++i) row_skip(mid_slot);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);  // row i1 was only ever a dn row
     }
+    // the J V stores still in flight read this CTA's shared memory: they must have completed before the CTA retires
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
   reduce_gram<NBLK, CW, NT>(acc, red, partials, ticket, Gout);
 }
@@ -1031,11 +1069,11 @@ EncodeTiledFn encode_tiled_fn() {
 }
 // tensor map over stored columns: [ncols][rows + 2 halo][m] doubles, column stride ld; box {pw, 1, ncol_box}
 int make_column_map(CUtensorMap* tm, const double* base, int m, int stored_rows, int64_t ld, int ncols, int ncol_box,
-                    int pw) {
+                    int pw, bool force_3d = false) {
   EncodeTiledFn enc = encode_tiled_fn();
   GNK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   CUresult r;
-  if (ncol_box > 1 || ncols > 1) {
+  if (ncol_box > 1 || ncols > 1 || force_3d) {
     cuuint64_t dims[3] = {(cuuint64_t)m, (cuuint64_t)stored_rows, (cuuint64_t)ncols};
     cuuint64_t strides[2] = {(cuuint64_t)m * 8, (cuuint64_t)ld * 8};
     cuuint32_t box[3] = {(cuuint32_t)pw, 1, (cuuint32_t)ncol_box};
@@ -1073,8 +1111,11 @@ int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, 
   if (int rc = make_column_map(&tmY, d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
   const bool has_e = prm->lam != 0.0;
   if (int rc = make_column_map(&tmE, has_e ? d_expu : d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
+  // J V: k columns of `rows` owned grid rows; the store box is one warp's piece {8 points, 1 row, 8 NB columns}
+  CUtensorMap tmJ;
+  if (int rc = make_column_map(&tmJ, d_JV, lay->m, lay->rows, ldjv, k, 8 * NB, 8, /*force_3d=*/true)) return rc;
   auto kern = stencil_gram_kernel<NB, CW>;
-  constexpr int dyn = sg_slot_bytes<NB, CW>() * sg_nslot<NB, CW>();
+  constexpr int dyn = sg_dyn_bytes<NB, CW>();
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
     GNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
@@ -1086,7 +1127,7 @@ int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, 
   const int64_t ntask = (int64_t)ntj * ceil_div(lay->rows, TI);
   const int ctas = (int)(ntask < ctx->sm_count ? ntask : ctx->sm_count);
   StencilPanel p{lay->m, lay->rows, k, has_e ? 1 : 0, ldjv, prm->c_lap, prm->c_adv, prm->lam, sign};
-  kern<<<ctas, 32 * (CW + 1), dyn, st>>>(tmV, tmY, tmE, p, TI, d_JV, base + CQ_PART, ctx->d_tickets + TK_CHOLQR,
+  kern<<<ctas, 32 * (CW + 1), dyn, st>>>(tmV, tmY, tmE, tmJ, p, TI, base + CQ_PART, ctx->d_tickets + TK_CHOLQR,
                                         base + CQ_LOCAL);
   GNK_LAUNCH_CHECK(ctx);
   return cholqr_tail<NB, RU>(ctx, d_JV, ldjv, lay->n_own, k, d_r + lay->off, sign_a, d_out, st);

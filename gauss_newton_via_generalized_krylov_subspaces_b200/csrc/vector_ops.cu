@@ -143,7 +143,11 @@ __device__ __forceinline__ void dots_pass(const double* __restrict__ Vb, int64_t
 __global__ void __launch_bounds__(TPB, 4) dots_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
                                                     const double* __restrict__ w, double* __restrict__ partials,
                                                     unsigned int* ticket, double* __restrict__ h, gnk_p2p_dev pd) {
-  __shared__ double sh[32];
+  // per-warp sums of every column; ONE barrier per launch instead of two per column (at n ~ 1e6 -- the 8-GPU slabs and
+  // the 1024^2 grid -- the 2 k barriers of the per-column block reductions were most of the kernel: 51 us for 20 us
+  // of traffic)
+  __shared__ double wpart[TPB / 32][GNK_MAX_BASIS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int jb = 0; jb < k; jb += JB) {
     double acc[JB];
 #pragma unroll
@@ -163,13 +167,20 @@ __global__ void __launch_bounds__(TPB, 4) dots_kernel(const double* __restrict__
 #pragma unroll
     for (int u = 0; u < JB; ++u) {
       if (u < nj) {
-        double r = block_sum(acc[u], sh);
-        if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * GNK_MAX_BASIS + jb + u] = r;
+        const double r = warp_sum(acc[u]);
+        if (lane == 0) wpart[wid][jb + u] = r;
       }
     }
   }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += TPB) {
+    double r = wpart[0][j];
+#pragma unroll
+    for (int q = 1; q < TPB / 32; ++q) r += wpart[q][j];  // fixed warp order: deterministic
+    partials[(int64_t)blockIdx.x * GNK_MAX_BASIS + j] = r;
+  }
   if (grid_arrive_last(ticket)) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nw = blockDim.x >> 5;
     for (int j = wid; j < k; j += nw) {
       double a = 0.0;
       for (int b = lane; b < (int)gridDim.x; b += 32) a += __ldcg(partials + (int64_t)b * GNK_MAX_BASIS + j);
@@ -334,7 +345,7 @@ int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, 
   GNK_REQUIRE(ctx && lay && d_V && d_w && d_h, "gnk_cgs_dots: null argument");
   GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_dots: k out of range");
   GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_dots: off/ld must be even");
-  int grid = stream_grid(ctx, lay->n_own / 2, 8);
+  int grid = stream_grid(ctx, lay->n_own / 8, 8);  // >= 4 double2 per thread before another CTA is added
   dots_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V + lay->off, lay->ld, lay->n_own, k, d_w + lay->off,
                                                       ctx->d_partials + PART_DOTS, ctx->d_tickets + TK_DOTS, d_h,
                                                       p2p_next(ctx));

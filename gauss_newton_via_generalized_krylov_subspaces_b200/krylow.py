@@ -159,6 +159,8 @@ class GeneralizedKrylowSubspace:
             pb.upload_x(x0, x)
         else:
             rt = get_runtime()
+            from .gauss_newton_krylow import require_single_rank_unless_sharded
+            require_single_rank_unless_sharded(rt, None, "GeneralizedKrylowSubspace.start")
             f = flat_layout_fields(x0.shape[0])
             self._setup(x0.shape[0], f, make_layout(f), _FlatOwner(rt, x0.shape[0]), self.capacity)
             x = rt.zeros(self.ld)

@@ -245,6 +245,34 @@ def ttt():
         ), y_sample=y[sample_idx(y.shape[0])], u0_sample=u0[sample_idx(u0.shape[0])])
 
 
+def cgx0():
+    """cg_least_squares with an initial guess (gauss_newton.py:14,46,56 forward x0 to scipy's cg): the Bratu Jacobian at
+    grid_nodes=34 and the chained Rosenbrock Jacobian, with and without the discarded unpreconditioned first run."""
+    from gauss_newton import cg_least_squares
+    flat = {}
+    pb, y, res, jac, err, u0 = bratu_setup(34, 5, 10)
+    rs = np.random.RandomState(11)
+    A = -1 * jac(u0)
+    r = res(u0)
+    guess = 1e-3 * rs.normal(size=u0.shape[0])
+    flat.update({"bratu/u": u0, "bratu/y": r, "bratu/x0": guess})
+    for pre in (True, False):
+        x, it = cg_least_squares(A, r, x0=guess.copy(), preconditioner=pre)
+        flat[f"bratu/x_pre{int(pre)}"] = x
+        flat[f"bratu/it_pre{int(pre)}"] = np.array(it)
+    xr = 1.0 + 0.1 * rs.normal(size=1000)
+    Ar = -1 * rosenbrock_problem.jac(xr)
+    rr = rosenbrock_problem.res(xr)
+    gr = 0.05 * rs.normal(size=1000)
+    flat.update({"rosen/x": xr, "rosen/x0": gr})
+    for pre in (True, False):
+        x, it = cg_least_squares(Ar, rr, x0=gr.copy(), preconditioner=pre)
+        flat[f"rosen/x_pre{int(pre)}"] = x
+        flat[f"rosen/it_pre{int(pre)}"] = np.array(it)
+    np.savez_compressed(os.path.join(OUT, "cg_x0.npz"), **flat)
+    print("cg_x0.npz written:", {k: int(v) for k, v in flat.items() if "/it_" in k})
+
+
 def sensitivity(G, name, runs_kw):
     """The reference against ITSELF when the start vector u0 is perturbed by one unit in the last place (relative
     2^-52, random signs, seed 7).  The deviation of the perturbed trace from the unperturbed one is the conditioning of
@@ -277,4 +305,4 @@ def sens4097():
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["small"]:
         dict(small=small, g1025=g1025, g4097=g4097, kernels=kernels_fixture, sens101=sens101, sens1025=sens1025,
-             sens4097=sens4097, ttt=ttt)[what]()
+             sens4097=sens4097, ttt=ttt, cgx0=cgx0)[what]()

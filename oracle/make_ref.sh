@@ -20,10 +20,12 @@ fi
 mkdir -p "$OUT"
 # the modules on the path: solver, Krylov state, line search, second solver (CGLS), result record, the two problems,
 # and the harness that the experiment scripts call the solvers through
-for f in gauss_newton_krylow.py krylow.py armijo_goldstein.py gauss_newton.py regression_result.py \
-         bratu_pde_problem.py rosenbrock_problem.py benchmark.py; do
+# ... plus the Bratu experiment script (workload driver of config 1), which tests/ runs UNCHANGED on top
+# of the B200 package (install_flat_names(), matplotlib mocked) to show that the reference's own driver drops in
+FILES="gauss_newton_krylow.py krylow.py armijo_goldstein.py gauss_newton.py regression_result.py \
+       bratu_pde_problem.py rosenbrock_problem.py benchmark.py bratu_pde_test.py"
+for f in $FILES; do
   install -m 0644 "$REF/$f" "$OUT/$f"
 done
-( cd "$REF" && sha256sum gauss_newton_krylow.py krylow.py armijo_goldstein.py gauss_newton.py regression_result.py \
-    bratu_pde_problem.py rosenbrock_problem.py benchmark.py ) > "$OUT/SHA256SUMS"
+( cd "$REF" && sha256sum $FILES ) > "$OUT/SHA256SUMS"
 echo "make_ref: $(ls "$OUT"/*.py | wc -l) reference modules -> $OUT"

@@ -35,12 +35,13 @@ class Recorder:
         self.xs.append(x[self.idx].copy())
 
 
-def sensitivity_bound(golden_run, perturbed_run, floor=1e-10, factor=100.0):
+def sensitivity_bound(golden_run, perturbed_run, floor=1e-10, factor=30.0):
     """Per-iteration tolerance for the large grids: the unmodified reference, re-run with its start vector perturbed by
     one unit in the last place (oracle/gen_golden.py:sensitivity), moves by env_i at iteration i.  An independent
     implementation is held to max(floor, factor * running max of env): i.e. to the 1e-10 bar wherever the reference's
     own trajectory is that well determined, and to a fixed multiple of its 1-ulp conditioning where it is not (a few
-    early iterations, where x = c * v0 is formed by cancellation).  Measured GPU/envelope ratios are <= 25."""
+    early iterations, where x = c * v0 is formed by cancellation).  Measured GPU/envelope ratios are <= 10 (printed by
+    ``check_trace`` / reported by bench.py's ``parity.max_dev_over_bound``: 0.31 of the bound at 4096^2)."""
     a, b = golden_run["xs"], perturbed_run["xs"]
     n = min(len(a), len(b))
     scale = np.max(np.abs(a[:n]), axis=1, keepdims=True)
@@ -68,6 +69,7 @@ def check_trace(rec, g, tol, upto=None, check_cg=False):
     tolv = np.broadcast_to(np.asarray(tol, dtype=np.float64), (n,)) if np.ndim(tol) == 0 else np.asarray(tol)[:n]
     assert np.all(dv <= tolv) and np.all(dnv <= tolv), (list(zip(dv, tolv))[:8], float(dv.max()), float(dnv.max()))
     d = float(dv.max())
+    print(f"[parity] {n} iterations: max deviation {d:.3e}, max deviation / tolerance {float(np.max(dv / tolv)):.3f}")
     if check_cg:
         assert list(rec.cg[:n]) == list(g["cg_iter"][:n])
     return d

@@ -79,6 +79,30 @@ def main():
         xs = np.array(rec.xs)
         d = np.max(np.abs(xs - gr["xs"]) / np.max(np.abs(gr["xs"]), axis=1, keepdims=True), axis=1)
         print(f"[multi] G=1025 world={world}: nit={out.nit} max dev {d.max():.2e} tail dev {d[4:].max():.2e} ok", flush=True)
+
+    # ---- the north-star workload itself: Bratu 4096^2, k = 1..30, golden trace of the reference --------------------
+    # (skipped with GNK_MULTI_SKIP_4096=1 for quick plumbing checks)
+    if os.environ.get("GNK_MULTI_SKIP_4096", "0") != "1":
+        gd, gs = Golden("bratu_g4097"), Golden("bratu_g4097_sens")
+        o = orc.BratuOracle(4097, 5, 10)
+        y, u0 = o.operator(o.u_true), o.start_vector(seed=42)
+        pb = g.BratuPdeProblem(4097, 5, 10)
+        res, jac, err = pb.make_res(y), pb.make_jac(), pb.make_error()
+        gr = gd.run("gnk_k30")
+        assert np.array_equal(u0[gr["sample_idx"]], gd["u0_sample"]) and np.array_equal(y[gr["sample_idx"]], gd["y_sample"])
+        rec = Recorder(gr["sample_idx"], err)
+        out = g.gauss_newton_krylow(res, u0, jac, callback=rec, max_iter=31)
+        check_trace(rec, gr, sensitivity_bound(gr, gs.run("gnk_k30")))
+        assert (out.nit, out.nrev, out.njev) == (30, 31, 30) and gather_equal(out.x)
+        xs = np.array(rec.xs)
+        d = np.max(np.abs(xs - gr["xs"]) / np.max(np.abs(gr["xs"]), axis=1, keepdims=True), axis=1)
+        assert d[12:].max() < 1e-10, d[12:].max()                       # the plain bar from iteration 13 on
+        loss = res.loss(out.x)
+        assert abs(loss - gr["loss"][-1]) <= 2e-10 * gr["loss"][-1]
+        if rank == 0:
+            print(f"[multi] G=4097 world={world}: nit={out.nit} max dev {d.max():.2e} tail dev {d[12:].max():.2e} "
+                  f"final loss dev {abs(loss - gr['loss'][-1]) / gr['loss'][-1]:.1e} ok", flush=True)
+    if rank == 0:
         print("MULTI_OK", flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -80,3 +80,44 @@ def test_sharded_gnk_matches_reference_golden(world, tmp_path):
         assert np.max(np.abs(z["xs"] - gr["xs"]) / scale) < 1e-8                       # restarts amplify rounding
     for z in outs[1:]:                                           # every rank holds the same global result, bit for bit
         assert np.array_equal(z["x"], outs[0]["x"]) and np.array_equal(z["xnorm"], outs[0]["xnorm"])
+
+
+def _replicated_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mock_backend
+    mock_backend.install()
+    import gauss_newton_via_generalized_krylov_subspaces_b200 as g
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import _lib, rosenbrock_problem as rp
+    raised = []
+    x0 = np.full(1000, 2.0)
+    for name, call in (
+            ("gnk", lambda: g.gauss_newton_krylow(rp.res, x0, rp.jac, callback=lambda **k: None, max_iter=4)),
+            ("gn", lambda: g.gauss_newton(rp.res, x0, rp.jac, callback=lambda **k: None, max_iter=4)),
+            ("lls", lambda: g.linear_least_squares(np.eye(4, 2), np.ones(4))),
+            ("cg", lambda: g.cg_least_squares(rp.jac(x0), rp.res(x0))),
+            ("krylow", lambda: g.GeneralizedKrylowSubspace().start(x0))):
+        try:
+            call()
+            raised.append((name, ""))
+        except _lib.GnkError as e:
+            raised.append((name, str(e)))
+    np.save(os.path.join(out_dir, f"g{rank}.npy"), np.array(raised))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicated_problems_refuse_a_multi_rank_process_group(tmp_path):
+    """advisor (round 1, medium): problems that are not row-sharded hold FULL vectors on every rank while the library
+    sums its reductions over all ranks (norms sqrt(W) too large, Armijo compares against W*g).  SURVEY 8e says
+    "replicas only" for them: every such entry point raises a clear error under a process group with more than one
+    rank instead of returning wrong numbers."""
+    mp.spawn(_replicated_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = np.load(os.path.join(tmp_path, f"g{r}.npy"))
+        assert len(got) == 5
+        for name, msg in got:
+            assert "not row-sharded" in msg, (name, msg)

@@ -441,6 +441,28 @@ def test_cgls_stencil_and_csr(g, precond):
     assert rel(xg, xr) < 1e-3
 
 
+@pytest.mark.parametrize("precond", [True, False])
+def test_cgls_with_initial_guess_matches_reference_golden(g, precond):
+    """cg_least_squares(A, y, x0=...): the reference forwards x0 to scipy's cg (gauss_newton.py:14,46,56).  Golden from
+    the unmodified reference (oracle/gen_golden.py cgx0): iteration counts (rounding-sensitive: +-2) and the solution."""
+    import scipy.sparse as sp
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cg_x0.npz"))
+    pb = g.BratuPdeProblem(34, 5, 10)
+    x, it = g.cg_least_squares(-1 * pb.make_jac()(z["bratu/u"]), z["bratu/y"], x0=z["bratu/x0"], preconditioner=precond)
+    assert abs(it - int(z[f"bratu/it_pre{int(precond)}"])) <= 2, (it, int(z[f"bratu/it_pre{int(precond)}"]))
+    assert rel(x, z[f"bratu/x_pre{int(precond)}"]) < 1e-6
+    x, it = g.cg_least_squares(sp.csr_array(-1 * rp.jac(z["rosen/x"])), rp.res(z["rosen/x"]), x0=z["rosen/x0"],
+                               preconditioner=precond)
+    assert abs(it - int(z[f"rosen/it_pre{int(precond)}"])) <= 1
+    assert rel(x, z[f"rosen/x_pre{int(precond)}"]) < 1e-6
+    # x0 = exact solution of a consistent system: zero iterations of the preconditioned run
+    xs = np.random.RandomState(5).normal(size=1000)
+    A = sp.csr_array(rp.jac(z["rosen/x"]))
+    x, it = g.cg_least_squares(A, A @ xs, x0=xs, preconditioner=True)
+    assert it == 0 and np.array_equal(x, xs)
+
+
 # ------------------------------------------------------------------------------------------------
 # public building blocks with the reference's signatures
 # ------------------------------------------------------------------------------------------------

@@ -404,3 +404,104 @@ def test_gnk_with_cgls_inner_solve(g):
     loose = g.gauss_newton_krylow(res, gd["u0"], jac, krylow_restart=50, max_iter=61, callback=lambda **k: None,
                                   ls_solver="cgls", cg_rtol=1e-4)
     assert abs(err(loose.x) - err(qr.x)) < 1e-3 * err(qr.x)
+
+
+# ------------------------------------------------------------------------------------------------
+# the experiment harness on live device vectors, and the reference's own driver script on this package
+# ------------------------------------------------------------------------------------------------
+def test_benchmark_method_keeps_vectors_on_the_device(g):
+    """benchmark_method (benchmark.py:30-55) calls error(x) and loss(x) at every callback: with the package's callables
+    both are evaluated on the callback's DeviceVector in HBM -- no iterate crosses PCIe during the solve (the only
+    downloads are 8-byte scalars); results equal the reference's golden curves."""
+    from gauss_newton_via_generalized_krylov_subspaces_b200.benchmark import benchmark_method
+    gd = Golden("bratu_g101")
+    pb, res, jac, err = _bratu(g, gd, 101)
+    d = pb.dev
+    moved = []
+    real_down, real_mat = d.download_global, g.DeviceVector.materialize
+    d.download_global = lambda col: (moved.append("download_global"), real_down(col))[1]
+    g.DeviceVector.materialize = lambda self: (moved.append("materialize"), real_mat(self))[1]
+    try:
+        u0 = d.resident(gd["u0"])              # the start vector already lives in HBM
+        e, l, nf, cg = benchmark_method(lambda r, x0, j, args, callback, **kw: g.gauss_newton_krylow(
+            r, x0, j, args=args, callback=callback, x_on_device=True, **kw), res, u0, jac, err,
+            kwargs=dict(max_iter=100))
+    finally:
+        d.download_global, g.DeviceVector.materialize = real_down, real_mat
+    assert moved == [], moved
+    gr = gd.run("gnk_res_old")
+    assert len(e) == 100 and nf == [2] + [1] * 98 and cg == []
+    assert np.allclose(e[1:], gr["err"], rtol=1e-9) and np.allclose(l[1:], gr["loss"], rtol=1e-9)
+    # the full-space solver through the same harness (cg_iter is reported, counts +-2 %)
+    e, l, nf, cg = benchmark_method(g.gauss_newton, res, gd["u0"], jac, err)
+    ggn = gd.run("gn")
+    assert len(cg) == len(ggn["cg_iter"]) and np.allclose(cg, ggn["cg_iter"], rtol=0.02)
+    assert e[-1] < 1e-10
+
+
+def test_reference_driver_script_runs_unchanged_on_this_package(g, capsys, monkeypatch, tmp_path):
+    """The reference's own experiment script bratu_pde_test.py (UNMODIFIED, from oracle/_ref) executed on top of this
+    package: install_flat_names() makes its bare imports (`from gauss_newton_krylow import gauss_newton_krylow`, ...)
+    resolve to the B200 modules, matplotlib is mocked.  compare() and compare_without_scaling() run
+    GN, GNK, GNK-(II) and the scipy comparison curve through benchmark_method; the curves they would plot are checked
+    against the goldens of the same runs."""
+    import runpy
+    import sys
+    from unittest import mock
+    from oracle import ref_loader
+    script = os.path.join(ref_loader.REF_DIR, "bratu_pde_test.py")
+    if not os.path.exists(script):
+        pytest.skip("oracle/_ref/bratu_pde_test.py has not been built (oracle/make_ref.sh needs /root/reference)")
+    plt = mock.MagicMock()
+    mpl = mock.MagicMock()
+    mpl.pyplot = plt      # `import matplotlib.pyplot as plt` binds the attribute of the parent module
+    mods = {"matplotlib": mpl, "matplotlib.pyplot": plt, "matplotlib.ticker": mpl.ticker, "matplotlib.cm": mpl.cm}
+    saved = {k: sys.modules.get(k) for k in list(mods) + list(g._MODULES)}
+    sys.modules.update(mods)
+    g.install_flat_names()
+    monkeypatch.chdir(tmp_path)
+    curves = {}
+    try:
+        ns = runpy.run_path(script, run_name="reference_bratu_pde_test")
+        assert ns["gauss_newton_krylow"] is g.gauss_newton_krylow and ns["BratuPdeProblem"] is g.BratuPdeProblem
+        plt.semilogy.side_effect = lambda data, *a, **kw: curves.setdefault(("err", kw.get("label")), list(data))
+        ns["compare"]()
+        default = dict(curves)
+        curves.clear()
+        ns["compare_without_scaling"]()
+        h1 = dict(curves)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    out = capsys.readouterr().out
+    assert "Compare default, mean cg iter = " in out and "Compare without scaling, mean cg iter = " in out
+    mean_cg = float(out.split("Compare default, mean cg iter = ")[1].split()[0])
+    assert abs(mean_cg - 1324.5) < 0.02 * 1324.5          # SURVEY 8c: cg_iter = [216, 1283, 1986, 1813]
+    gd, gh = Golden("bratu_g101"), Golden("bratu_g101_h1")
+    for curves_, gold in ((default, gd), (h1, gh)):
+        gnk, gnk2, gn = curves_[("err", "GNK")], curves_[("err", "GNK-(II)")], curves_[("err", "Gauß-Newton")]
+        assert np.allclose(gnk[1:], gold.run("gnk_res_old")["err"], rtol=1e-7)
+        assert np.allclose(gnk2[1:], gold.run("gnk_res_new")["err"], rtol=1e-7)
+        assert len(gn) - 1 == len(gold.run("gn")["err"]) and gn[-1] < 1e-9
+        assert len(curves_[("err", "Referenz")]) > 3      # scipy.optimize.least_squares ran on the assembled CSR
+    assert len(h1[("err", "GNK")]) - 1 == 82 and len(h1[("err", "GNK-(II)")]) - 1 == 56   # the converging config
+
+
+@pytest.mark.parametrize("G", [257, 513, 1025])
+def test_time_to_tolerance_configs_converge_like_the_reference(g, G):
+    """grid_resolution=1, version="res_new" on larger grids (oracle/gen_golden.py ttt): the runs bench.py times as
+    time-to-tolerance.  Same stop iteration, success, nfev; iterates within the first-cycle bar."""
+    gd = Golden(f"bratu_g{G}_h1")
+    gr = gd.run("gnk_res_new")
+    o = orc.BratuOracle(G, 5, 10, h=1)
+    y, u0 = o.operator(o.u_true), o.start_vector(seed=42)
+    assert np.array_equal(u0[gr["sample_idx"]], gd["u0_sample"]) and np.array_equal(y[gr["sample_idx"]], gd["y_sample"])
+    pb = g.BratuPdeProblem(G, 5, 10, grid_resolution=1)
+    rec = Recorder(gr["sample_idx"], pb.make_error())
+    out = g.gauss_newton_krylow(pb.make_res(y), u0, pb.make_jac(), callback=rec, version="res_new", max_iter=100)
+    assert (out.nit, out.nrev, bool(out.success)) == (int(gr["nit"]), int(gr["nfev"]), True)
+    check_trace(rec, gr, 1e-9)
+    assert abs(rec.err[-1] - gr["err"][-1]) < 1e-6 * max(gr["err"][-1], 1e-6) + 1e-12

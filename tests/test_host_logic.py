@@ -342,3 +342,119 @@ def test_device_side_error_and_loss_in_callbacks(g):
     gr = gd.run("gnk_res_old")
     assert np.allclose(a[:, 0], a[:, 1], rtol=1e-13) and np.allclose(a[:, 2], a[:, 3], rtol=1e-12)
     assert np.allclose(a[:, 0], gr["err"][:5], rtol=1e-10) and np.allclose(a[:, 2], gr["loss"][:5], rtol=1e-10)
+
+
+def test_callback_that_keeps_x_gets_a_snapshot(g):
+    """Ownership hand-off of the callback's DeviceVector (device.DeviceVector.settle): a callback that KEEPS x -- in a
+    list, behind a wrapper, in a closure -- must later still read the iterate of that iteration, although the solver
+    reuses the device buffer; a callback that drops x costs no download.  No reference counts are inspected."""
+    gd = Golden("bratu_g34")
+    pb = g.BratuPdeProblem(34, 5, 10)
+    res, jac = pb.make_res(gd["y"]), pb.make_jac()
+    kept, copies = [], []
+
+    def keeps(x, nfev, cg_iter):
+        kept.append(x)                           # no copy: the DeviceVector itself
+
+    def wrapped(**kw):                           # an extra frame / an extra reference while the callback runs
+        holder = [kw["x"]]
+        keeps(**kw)
+        del holder
+
+    g.gauss_newton_krylow(res, gd["u0"], jac, callback=wrapped, max_iter=8)
+    g.gauss_newton_krylow(res, gd["u0"], jac, callback=lambda x, nfev, cg_iter: copies.append(np.array(x)), max_iter=8)
+    assert len(kept) == len(copies) == 7
+    for a, b in zip(kept, copies):
+        assert isinstance(a, g.DeviceVector) and a._host is not None     # snapshot taken when the callback returned
+        assert np.array_equal(np.asarray(a), b)
+    # a callback that ignores x: nothing is downloaded
+    rt = g.get_runtime()
+    n_down = [0]
+    real = pb.dev.download_global
+    pb.dev.download_global = lambda col: (n_down.__setitem__(0, n_down[0] + 1), real(col))[1]
+    g.gauss_newton_krylow(res, gd["u0"], jac, callback=lambda **kw: None, max_iter=8, x_on_device=True)
+    assert n_down[0] == 0
+    # same contract in the full-space solver (gauss_newton.py:125-127 hands the SAME array every time; here each
+    # callback gets its own lazy vector)
+    kept2 = []
+    out = g.gauss_newton(res, gd["u0"], jac, callback=lambda x, nfev, cg_iter: kept2.append(x), max_iter=4)
+    assert all(v._host is not None for v in kept2) and np.array_equal(np.asarray(kept2[-1]), out.x)
+
+
+def test_device_vector_as_x0_of_a_foreign_problem(g):
+    """a DeviceVector is an ordinary array-like for every problem but the one that made it (advisor, round 1: it used
+    to be materialised by np.asarray and then dereferenced as a NULL device pointer)"""
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
+    pb = g.BratuPdeProblem(34, 5, 10)
+    x0 = np.full(1089, 2.0)
+    x0[2] = 1.99
+    dv = pb.dev.resident(x0)                       # lives on the device, made by ANOTHER problem
+    p = 1089
+
+    def res(x):
+        return np.concatenate([10 * (x[1:] - x[:-1] ** 2), 1 - x[:-1]])
+
+    def jac(x):
+        import scipy.sparse as sp
+        b1 = 10 * sp.eye(p - 1, p, k=1) - 20 * sp.diags(x[:-1], shape=(p - 1, p))
+        return sp.vstack([b1, -sp.eye(p - 1, p)]).tocsr()
+
+    a = g.gauss_newton_krylow(res, dv, jac, callback=lambda **k: None, max_iter=6)
+    b = g.gauss_newton_krylow(res, x0, jac, callback=lambda **k: None, max_iter=6)
+    assert np.array_equal(a.x, b.x) and a.nit == b.nit
+
+
+def test_cg_least_squares_with_initial_guess(g):
+    """cg_least_squares(A, y, x0=...) -- the reference forwards x0 to scipy's cg (gauss_newton.py:14,46,56); golden
+    from the unmodified reference (oracle/gen_golden.py cgx0): same iteration counts, same solution."""
+    from oracle import gnk_oracle as orc
+    import scipy.sparse as sp
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cg_x0.npz"))
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
+    o = orc.BratuOracle(34, 5, 10)
+    A = -1 * o.make_jac()(z["bratu/u"])
+    pb = g.BratuPdeProblem(34, 5, 10)
+    Ad = -1 * pb.make_jac()(z["bratu/u"])
+    Ar = sp.csr_array(-1 * rp.jac(z["rosen/x"]))
+    rr = rp.res(z["rosen/x"])
+    for pre in (True, False):
+        # the oracle restatement against the reference
+        x, it = orc.cgls(A, z["bratu/y"], preconditioner=pre, x0=z["bratu/x0"])
+        assert it == int(z[f"bratu/it_pre{int(pre)}"]) and rel(x, z[f"bratu/x_pre{int(pre)}"]) < 1e-10
+        x, it = orc.cgls(Ar, rr, preconditioner=pre, x0=z["rosen/x0"])
+        assert it == int(z[f"rosen/it_pre{int(pre)}"]) and rel(x, z[f"rosen/x_pre{int(pre)}"]) < 1e-10
+        # the package's entry point (host logic through the mock; the CUDA path is tests/test_gpu_kernels.py)
+        x, it = g.cg_least_squares(Ad, z["bratu/y"], x0=z["bratu/x0"], preconditioner=pre)
+        assert abs(it - int(z[f"bratu/it_pre{int(pre)}"])) <= 2 and rel(x, z[f"bratu/x_pre{int(pre)}"]) < 1e-6
+        x, it = g.cg_least_squares(Ar, rr, x0=z["rosen/x0"], preconditioner=pre)
+        assert abs(it - int(z[f"rosen/it_pre{int(pre)}"])) <= 1 and rel(x, z[f"rosen/x_pre{int(pre)}"]) < 1e-6
+
+
+def test_reference_modules_pin_the_oracle():
+    """oracle/_ref (built by oracle/make_ref.sh from /root/reference; absent on a box that never saw the reference):
+    the files are the reference's, byte for byte, and the oracle port reproduces a run of the imported reference."""
+    from oracle import ref_loader, gnk_oracle as orc
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref has not been built (no /root/reference here)")
+    import hashlib
+    sums = dict(line.split()[::-1] for line in open(os.path.join(ref_loader.REF_DIR, "SHA256SUMS")))
+    for name, digest in sums.items():
+        assert hashlib.sha256(open(os.path.join(ref_loader.REF_DIR, name), "rb").read()).hexdigest() == digest
+        if os.path.isdir("/root/reference"):
+            assert open(os.path.join(ref_loader.REF_DIR, name), "rb").read() == open(f"/root/reference/{name}", "rb").read()
+    ref = ref_loader.load_reference()
+    import sys
+    assert "krylow" not in sys.modules or "_ref" not in getattr(sys.modules["krylow"], "__file__", "")
+    pb = ref.bratu_pde_problem.BratuPdeProblem(34, 5, 10)
+    y = pb.pde_operator(pb.u_true)
+    np.random.seed(42)
+    u0 = pb.u_true + 0.1 * np.random.normal(loc=0, scale=1, size=pb.u_true.shape[0])
+    xs = []
+    out = ref.gauss_newton_krylow.gauss_newton_krylow(pb.make_res(y), u0, pb.make_jac(), max_iter=15,
+                                                      callback=lambda x, nfev, cg_iter: xs.append(x.copy()))
+    o = orc.BratuOracle(34, 5, 10)
+    assert np.array_equal(o.operator(o.u_true), y) and np.array_equal(o.start_vector(seed=42), u0)
+    xo = []
+    po = orc.gnk(o.make_res(y), u0, o.make_jac(), max_iter=15, callback=lambda x, nfev, cg_iter: xo.append(x.copy()))
+    assert (po["nit"], po["nfev"], po["njev"]) == (out.nit, out.nrev, out.njev)
+    assert max(rel(a, b) for a, b in zip(xo, xs)) < 1e-11
