@@ -53,6 +53,7 @@ SIGNATURES = {
     "gnk_stencil_apply": (_I, [_P, _LP, _BP, _P, _P, _L, _I, _D, _I, _P, _L, _L, _P]),
     "gnk_stencil_normal_diag": (_I, [_P, _LP, _BP, _P, _P, _P]),
     "gnk_combine": (_I, [_P, _LP, _P, _I, _P, _P, _D, _P, _P]),
+    "gnk_combine_step": (_I, [_P, _LP, _P, _I, _P, _P, _D, _P, _P, _P, _P]),
     "gnk_norm_stats": (_I, [_P, _LP, _P, _P, _P]),
     "gnk_normalize": (_I, [_P, _LP, _P, _P, _D, _P, _P, _P]),
     "gnk_cgs_dots": (_I, [_P, _LP, _P, _I, _P, _P, _P]),

@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
                                                             const double* __restrict__ Tg,
                                                             const double* __restrict__ d0g,
                                                             const double* __restrict__ aux,
-                                                            const int* __restrict__ status, double* __restrict__ out,
-                                                            gnk_p2p_dev pd) {
+                                                            const int* __restrict__ status, int have_g2,
+                                                            double* __restrict__ out, gnk_p2p_dev pd) {
   __shared__ double R2s[MAXC * GLD];
   __shared__ double R1s[MAXC * GLD];
   __shared__ double Rs[MAXC * GLD];
@@ -544,7 +544,10 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
     nparts = 1;
   }
   const int mode = *status;
-  if (mode == 1) {
+  if (mode == 1 || (mode == 2 && !have_g2)) {
+    // refused by the pivot floor -- or too ill-conditioned for the refinement form while the second CholeskyQR2 pass
+    // was not run (it is no longer part of the default chain: no Bratu run needs it, and its no-op launch cost 2.5 us
+    // per outer iteration); the host re-issues the solve with the Householder path either way
     write_refusal(k, out);
     return;
   }
@@ -718,8 +721,8 @@ int cholqr_tail(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, in
                                           sign, method, base + CQ_T, base + CQ_R1, base + CQ_D0, base + CQ_AUX, status,
                                           pd1);
   GNK_LAUNCH_CHECK(ctx);
-  // pass 2: the status word picks ONE of the two kernels, the other returns at once (the host does not know which:
-  // no read-back); one gather serves both
+  // pass 2: the refinement form by default (it returns at once unless the status word says 0); the second CholeskyQR2
+  // pass only when the caller asked for it (gnk_tsqr_ls_method 2)
   if (method == 0) {
     int rc;
     if (k <= 8) rc = launch_refine<8>(ctx, src, sign, base, status, st);
@@ -728,15 +731,18 @@ int cholqr_tail(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, in
     else rc = launch_refine<32>(ctx, src, sign, base, status, st);
     if (rc) return rc;
   }
-  cholqr_gram2_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_T, status, base + CQ_PART,
-                                                         ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL2 + GPAD);
-  GNK_LAUNCH_CHECK(ctx);
+  if (method == 2) {
+    cholqr_gram2_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_T, status, base + CQ_PART,
+                                                           ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL2 + GPAD);
+    GNK_LAUNCH_CHECK(ctx);
+  }
   const gnk_p2p_dev pd2 = multi ? p2p_next(ctx) : none;
   const bool gather2 = multi && !pd2.peers;
   if (gather2)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL2, base + CQ_ALL2, GPAD + NE, st)) return rc;
   cholqr_factor2_kernel<<<1, FT, 0, st>>>(gather2 ? base + CQ_ALL2 : base + CQ_LOCAL2, gather2 ? ctx->nranks : 1, NB, k,
-                                          base + CQ_R1, base + CQ_T, base + CQ_D0, base + CQ_AUX, status, d_out, pd2);
+                                          base + CQ_R1, base + CQ_T, base + CQ_D0, base + CQ_AUX, status,
+                                          method == 2 ? 1 : 0, d_out, pd2);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -21,13 +21,29 @@ __device__ __forceinline__ double2 ld2_stream(const double* p) {
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 
 // ---------------------------------------------------------------------------------------------
+// c_out (optional): CTA 0 also writes the coordinates of the point it forms, c_out[j] = c[j] + s d[j] (j < k) and
+// c_out[k] = 0 -- the accepted trial's x_coordinate with the entry of the next basis column already appended
+// (gauss_newton_krylow.py:98,124) -- and cprev2 = sum_j c[j]^2 for the stop test (:96-97).  Saves three tiny launches
+// per outer iteration.
 __global__ void __launch_bounds__(TPB) combine_kernel(const double* __restrict__ V, int64_t ld, int64_t len,
                                                        int k, const double* __restrict__ c,
                                                        const double* __restrict__ d, double s,
-                                                       double* __restrict__ x) {
+                                                       double* __restrict__ x, double* __restrict__ c_out,
+                                                       double* __restrict__ cprev2) {
   __shared__ double coef[GNK_MAX_BASIS];
   for (int j = threadIdx.x; j < k; j += blockDim.x) coef[j] = d ? (c[j] + s * d[j]) : c[j];
   __syncthreads();
+  if (blockIdx.x == 0) {
+    if (c_out) {
+      for (int j = threadIdx.x; j <= k && j < GNK_MAX_BASIS; j += blockDim.x) c_out[j] = (j < k) ? coef[j] : 0.0;
+    }
+    if (cprev2 && threadIdx.x < 32) {
+      double a = 0.0;
+      for (int j = threadIdx.x; j < k; j += 32) a = fma(c[j], c[j], a);
+      a = warp_sum(a);
+      if (threadIdx.x == 0) cprev2[0] = a;
+    }
+  }
   const int64_t nv = len >> 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
@@ -309,15 +325,21 @@ inline int stream_grid(const gnk_ctx* ctx, int64_t items, int per_sm) {
 
 extern "C" {
 
-int gnk_combine(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_c,
-                const double* d_d, double s, double* d_x, void* stream) {
+int gnk_combine_step(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_c,
+                     const double* d_d, double s, double* d_x, double* d_c_out, double* d_cprev2, void* stream) {
   GNK_REQUIRE(ctx && lay && d_V && d_c && d_x, "gnk_combine: null argument");
   GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_combine: k out of range");
   GNK_REQUIRE((lay->ld & 1) == 0, "gnk_combine: ld must be even");
+  GNK_REQUIRE(d_c_out != d_c, "gnk_combine_step: c_out must not alias c (rejected trials re-read c)");
   int grid = stream_grid(ctx, lay->ld / 2, 8);
-  combine_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V, lay->ld, lay->ld, k, d_c, d_d, s, d_x);
+  combine_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V, lay->ld, lay->ld, k, d_c, d_d, s, d_x, d_c_out, d_cprev2);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
+}
+
+int gnk_combine(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_c,
+                const double* d_d, double s, double* d_x, void* stream) {
+  return gnk_combine_step(ctx, lay, d_V, k, d_c, d_d, s, d_x, nullptr, nullptr, stream);
 }
 
 int gnk_norm_stats(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, double* d_stats, void* stream) {

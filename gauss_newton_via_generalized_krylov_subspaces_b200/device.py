@@ -129,6 +129,25 @@ class Runtime:
         self.sync()
         return self._pinned_np[:n].copy()
 
+    def mark_event(self):
+        """record an event on the current stream (one reusable event: the solvers keep at most one read in flight)"""
+        if getattr(self, "_event", None) is None:
+            self._event = self.torch.cuda.Event()
+            self._side = self.torch.cuda.Stream(device=self.device)
+        self._event.record()
+        return self._event
+
+    def read_at(self, t, count, event):
+        """``read`` that waits only for the work enqueued BEFORE ``event`` (mark_event): the copy runs on a side stream,
+        so kernels enqueued on the main stream after the event keep the device busy while the host waits for the
+        scalars (gauss_newton_krylow's speculative basis expansion)."""
+        side = self._side
+        side.wait_event(event)
+        with self.torch.cuda.stream(side):
+            self._pinned[:count].copy_(t[:count], non_blocking=True)
+        side.synchronize()
+        return self._pinned_np[:count].copy()
+
     def read_i32(self, t):
         self._pinned_i[:t.numel()].copy_(t, non_blocking=True)
         self.sync()

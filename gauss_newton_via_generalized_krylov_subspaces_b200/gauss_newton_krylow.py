@@ -37,7 +37,9 @@ _NB = _lib.GNK_MAX_BASIS
 _SC_LOSS = 2 * _NB + 8   # 2 doubles: sum(F^2) [, max|F|]
 _SC_CPREV = _SC_LOSS + 2  # sum(c_prev^2)
 _SC_FLAG = _SC_CPREV + 2   # int32 in a double slot: the deferred Krylov breakdown flag (krylow.dev_update)
+_SC_FLAG2 = _SC_CPREV + 3  # the same for a speculatively enqueued expansion (moved to _SC_FLAG when it is committed)
 _BLK = _SC_CPREV + 6
+_VERSIONS = ("res_old", "res_new", "jac_old_res_old", "jac_old_res_new")
 
 
 def resolve_problem(res, jac, x0, args, native_rosenbrock=False):
@@ -252,7 +254,10 @@ def gauss_newton_krylow(
 
     blk = rt.zeros(_BLK)            # [d(k) | g | resid2 | ndef | dnorm2 | diagR(k) ... | loss(2) | cprev2]
     loss_slot = blk[_SC_LOSS:_SC_LOSS + 2]
-    c = rt.zeros(_NB)
+    # coordinates: the current point's c and the trial's c + s d, which gnk_combine_step leaves on the device (with the
+    # next column's zero entry appended, :124); accepting a trial swaps the two -- no k-sized kernel is launched
+    cbuf = [rt.zeros(_NB), rt.zeros(_NB)]
+    c, c_next = cbuf
     one = rt.pinned(1)
 
     def set_c0(value):
@@ -344,14 +349,43 @@ def gauss_newton_krylow(
                 cgls_dense(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, cg_rtol, blk)
             else:
                 raise ValueError("ls_solver must be 'qr' or 'cgls'")
-            _lib.check(lib.gnk_dot(rt.ctx, k, ptr(c), ptr(c), ptr(blk, _SC_CPREV), rt.stream), "gnk_dot")
+            # Speculative basis expansion: everything the expansion needs -- J at the trial point (e^x is a by-product
+            # of the trial's residual kernel), the residuals -- exists once the FIRST trial has been enqueued, and in
+            # every Bratu / Rosenbrock run measured that trial is accepted.  So -J^T r, the Gram-Schmidt pass and the
+            # normalisation are enqueued BEHIND the trial and BEFORE the host reads the trial's loss: the device keeps
+            # working while the host waits for the scalars, judges the trial, runs the callback and enqueues the next
+            # iteration's least squares.  A rejected first trial simply does not commit the expansion (it is redone
+            # after the accepted trial; w, h, column k and the flag slot are overwritten).  Only with device-native
+            # residual / Jacobian (no host evaluation in between) and when the breakdown flag may be read late.
+            spec_ok = (native and defer_ok and iter + 1 < max_iter and iter % krylow_restart != 0
+                       and version in _VERSIONS and krylow.k < prob.p_glob
+                       and os.environ.get("GNK_SPECULATE", "1") != "0")
+            state["spec"] = None
+
+            def expansion_operands(jac_new):
+                if version == "res_old":
+                    return jac_new, F_cur
+                if version == "res_new":
+                    return jac_new, F_trial
+                if version == "jac_old_res_old":
+                    return jac_ev, F_cur
+                return jac_ev, F_trial
 
             # Armijo-Goldstein in coordinate space  (:91-93)
             def trial_loss(s):
-                krylow.dev_combine(c, blk, s, x_trial)
+                krylow.dev_combine(c, blk, s, x_trial, c_out=c_next, cprev2=ptr(blk, _SC_CPREV))
                 with rt.mark("residual", 32.0 * n_res_own):
                     prob.residual(x_trial, F_trial, loss_slot, aux=aux[1])
-                state["vals"] = rt.read(blk, _BLK)
+                if spec_ok and state["spec"] is None:
+                    ev = rt.mark_event()       # the scalars of this trial are complete here ...
+                    jac_new = prob.jacobian(x_trial, aux=aux[1])
+                    krylow.dev_expand_enqueue(*expansion_operands(jac_new), hx, ptr(blk, _SC_FLAG2))
+                    state["spec"] = jac_new
+                    state["vals"] = rt.read_at(blk, _BLK, ev)   # ... and are read while the expansion runs
+                else:
+                    if state["spec"] is not None:
+                        state["spec"] = False  # a later trial: the speculation belonged to a rejected one
+                    state["vals"] = rt.read(blk, _BLK)
                 if state["pending"] and state["vals"][_SC_FLAG:_SC_FLAG + 1].view(np.int32)[0] != 0:
                     raise _DeferredBreakdown()
                 if ls_solver == "qr" and ls_refused(state["vals"], k):
@@ -389,8 +423,8 @@ def gauss_newton_krylow(
         squared_sum_d = float(vals[k + 3])
         squared_sum_x_prev = float(vals[_SC_CPREV])
 
-        # c += s d  (:98)
-        _lib.check(lib.gnk_axpby(rt.ctx, k, 1.0, ptr(c), float(step_length), ptr(blk), ptr(c), rt.stream), "gnk_axpby")
+        # c += s d  (:98): the accepted trial's coordinates are already on the device
+        c, c_next = c_next, c
 
         xv = DeviceVector(prob, x_trial, prob.p_glob)
         callback(x=xv, nfev=nfev, cg_iter=None)
@@ -403,7 +437,8 @@ def gauss_newton_krylow(
             break
 
         jac_ev_old = jac_ev
-        jac_ev = prob.jacobian(x_trial, aux=aux[1])  # e^x came out of the accepted trial
+        speculated = state["spec"] is not None and state["spec"] is not False
+        jac_ev = state["spec"] if speculated else prob.jacobian(x_trial, aux=aux[1])  # e^x came out of the trial
         njev += 1
 
         # defer the breakdown read-back unless this iteration is the last one or ends with a restart (the message
@@ -411,7 +446,12 @@ def gauss_newton_krylow(
         defer = defer_ok and iter + 1 < max_iter and iter % krylow_restart != 0
         dflag = ptr(blk, _SC_FLAG) if defer else None
         try:
-            if version == "res_old":
+            if speculated:
+                # the expansion was enqueued behind the accepted trial; its flag sits in the second slot and moves to
+                # the slot the next iteration inspects
+                blk[_SC_FLAG:_SC_FLAG + 1].copy_(blk[_SC_FLAG2:_SC_FLAG2 + 1], non_blocking=True)
+                krylow.commit()
+            elif version == "res_old":
                 krylow.dev_update(jac_ev, F_cur, hx, dflag)
             elif version == "res_new":
                 krylow.dev_update(jac_ev, F_trial, hx, dflag)
@@ -424,7 +464,6 @@ def gauss_newton_krylow(
                     "Variable version must be in ['res_old','res_new','jac_old_res_old','jac_old_res_new']"
                 )
             state["pending"] = defer
-            c[krylow.k - 1:krylow.k].zero_()  # x_coordinate = np.append(x_coordinate, 0)   (:124)
         except GeneralizedKrylowSubspaceBreakdown:
             print(
                 f"Generalized krylow subspace breakdown at iteration = {iter}, basis.shape = ({prob.p_glob}, {krylow.k})"

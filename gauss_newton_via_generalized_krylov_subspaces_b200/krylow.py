@@ -95,19 +95,22 @@ class GeneralizedKrylowSubspace:
         self.k = 1
         return math.sqrt(ss[0])
 
-    def dev_combine(self, c, d, s, out):
-        """out = V_k (c + s d) over the whole stored column (krylow.py:41-42)."""
+    def dev_combine(self, c, d, s, out, c_out=None, cprev2=None):
+        """out = V_k (c + s d) over the whole stored column (krylow.py:41-42); optionally the coordinates c + s d (with
+        the next column's zero entry appended) and sum(c^2) are left on the device (gnk_combine_step)."""
         rt = self.rt
         with rt.mark("combine", 8.0 * self.fields["n_own"] * (self.k + 1)):
-            _lib.check(rt.lib.gnk_combine(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(c), ptr(d), float(s),
-                                          ptr(out), rt.stream), "gnk_combine")
+            _lib.check(rt.lib.gnk_combine_step(rt.ctx, C.byref(self.lay), ptr(self.V), self.k, ptr(c), ptr(d), float(s),
+                                               ptr(out), ptr(c_out), cprev2 if cprev2 is not None else ptr(None),
+                                               rt.stream), "gnk_combine")
 
-    def dev_update(self, jac_op, r, halo_exchange=None, deferred_flag=None):
-        """Expand the basis with -J^T r orthogonalised against V_k (krylow.py:55-73).  Raises the same
-        exceptions as the reference; on Breakdown the basis is left unchanged.
-        ``deferred_flag`` (a device pointer to an int32): the breakdown flag of krylow.py:66 is written there and NOT
-        read back; the column is appended speculatively and the caller inspects the flag with its next read-back
-        (one host synchronisation less per outer iteration) and calls ``retract()`` if it was set."""
+    def dev_expand_enqueue(self, jac_op, r, halo_exchange=None, flag_ptr=None):
+        """Enqueue the basis expansion with -J^T r orthogonalised against V_k (krylow.py:55-73) WITHOUT committing it:
+        the normalised vector lands in column k of the storage, the breakdown flag of krylow.py:66 in ``flag_ptr`` (a
+        device int32; default: this object's own flag), and ``k`` is unchanged until ``commit()``.  Nothing is read
+        back, so the caller may enqueue it speculatively (gauss_newton_krylow does, before it knows whether the Armijo
+        trial is accepted) -- an expansion that is not committed leaves no trace: w, h, the statistics, column k and the
+        flag are all overwritten by the next one."""
         if self.k == self.n_glob:
             raise GeneralizedKrylowSubspaceSpansEntireSpace
         rt, lib = self.rt, self.rt.lib
@@ -130,15 +133,29 @@ class GeneralizedKrylowSubspace:
         new = self.col(self.k)
         with rt.mark("normalize", 16.0 * n):
             _lib.check(lib.gnk_normalize(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8, ptr(new),
-                                         ptr(self.flag) if deferred_flag is None else deferred_flag, rt.stream),
+                                         ptr(self.flag) if flag_ptr is None else flag_ptr, rt.stream),
                        "gnk_normalize")
-        if deferred_flag is None and int(rt.read_i32(self.flag)[0]) != 0:
+        if halo_exchange is not None:
+            # a breakdown leaves column k unwritten; exchanging its halo rows anyway is harmless (the column is not
+            # part of the basis then) and keeps every rank in the same sequence of collectives
+            halo_exchange(self.V, 2, self.k * self.ld)
+
+    def commit(self):
+        """make the column written by the last ``dev_expand_enqueue`` part of the basis"""
+        self.k += 1
+
+    def dev_update(self, jac_op, r, halo_exchange=None, deferred_flag=None):
+        """Expand the basis with -J^T r orthogonalised against V_k (krylow.py:55-73).  Raises the same
+        exceptions as the reference; on Breakdown the basis is left unchanged.
+        ``deferred_flag`` (a device pointer to an int32): the breakdown flag of krylow.py:66 is written there and NOT
+        read back; the column is appended speculatively and the caller inspects the flag with its next read-back
+        (one host synchronisation less per outer iteration) and calls ``retract()`` if it was set."""
+        self.dev_expand_enqueue(jac_op, r, halo_exchange, deferred_flag)
+        if deferred_flag is None and int(self.rt.read_i32(self.flag)[0]) != 0:
             raise GeneralizedKrylowSubspaceBreakdown(
                 "Normal residual is allready inside generalized Krylow Subspcae, there for gauss newton krylow "
                 "algorithm has to proceed without enlarging the subspace.")
-        if halo_exchange is not None:
-            halo_exchange(self.V, 2, self.k * self.ld)
-        self.k += 1
+        self.commit()
 
     def retract(self):
         """undo a speculative append whose deferred breakdown flag turned out to be set (the column was not written)"""

@@ -92,6 +92,12 @@ int gnk_stencil_normal_diag(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu
  * d_d may be NULL (x = V_k c).  c, d are device vectors of length k. */
 int gnk_combine(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_c,
                 const double* d_d, double s, double* d_x, void* stream);
+/* gnk_combine that also leaves the coordinate bookkeeping of the outer iteration on the device (gauss_newton_krylow.py
+ * :96-98,124), so that no k-sized kernel has to be launched for it: d_c_out[j] = c[j] + s d[j] for j < k and
+ * d_c_out[k] = 0 (the trial's x_coordinate with the entry of the next basis column appended; GNK_MAX_BASIS doubles,
+ * must not alias d_c; may be NULL), *d_cprev2 = sum_j c[j]^2 (may be NULL). */
+int gnk_combine_step(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_c,
+                     const double* d_d, double s, double* d_x, double* d_c_out, double* d_cprev2, void* stream);
 /* d_stats[0] = sum of squares, d_stats[1] = max |.| over the owned part of a stored column
  * (krylow.py:31,36,66,71). */
 int gnk_norm_stats(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, double* d_stats, void* stream);

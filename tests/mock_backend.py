@@ -131,13 +131,23 @@ class MockLib:
 
     # ---- basis ----
     def gnk_combine(self, ctx, lay, V, k, c, d, s, x, stream):
+        return self.gnk_combine_step(ctx, lay, V, k, c, d, s, x, None, None, stream)
+
+    def gnk_combine_step(self, ctx, lay, V, k, c, d, s, x, c_out, cprev2, stream):
         lay = obj(lay)
         self.launches += 1
-        coef = arr(c, k).copy()
+        cv = arr(c, k).copy()
+        coef = cv.copy()
         if not isnull(d):
             coef = coef + s * arr(d, k)
         Vm = arr(V, lay.ld * k).reshape(k, lay.ld)
         arr(x, lay.ld)[:] = coef @ Vm
+        if not isnull(c_out):
+            o = arr(c_out, k + 1)
+            o[:k] = coef
+            o[k] = 0.0
+        if not isnull(cprev2):
+            arr(cprev2, 1)[0] = np.dot(cv, cv)
         return 0
 
     def gnk_norm_stats(self, ctx, lay, x, stats, stream):
@@ -428,6 +438,12 @@ class MockRuntime(device.Runtime):
 
     def host_register(self, addr, nbytes):
         pass
+
+    def mark_event(self):
+        return None
+
+    def read_at(self, t, count, event):
+        return self.read(t, count)
 
     def launches(self):
         return self.lib.launches
