@@ -412,6 +412,8 @@ class Harness:
                  max_dev=float(dev.max()), max_dev_first_cycle=float(dev[:first_cycle].max()),
                  max_dev_tail=float(dev[min(12, ncmp - 1):first_cycle].max()) if first_cycle > 12 else None,
                  max_dev_over_bound=float(np.max(dev / bound)), within_bound=bool(np.all(dev <= bound)),
+                 dev_per_iteration=[float(f"{v:.3e}") for v in dev],
+                 bound_per_iteration=[float(f"{v:.3e}") for v in bound],
                  bound="per iteration max(1e-10, 30 x the reference's own 1-ulp envelope) (tests/golden_util.py)",
                  final_loss=float(loss), golden_final_loss=gl,
                  final_loss_dev=None if gl is None else float(abs(loss - gl) / gl))

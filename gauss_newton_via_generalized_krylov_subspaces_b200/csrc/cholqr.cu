@@ -795,17 +795,11 @@ template <int CW> __host__ __device__ constexpr int sg_ye_bytes() { return (sg_p
 template <int NB, int CW> __host__ __device__ constexpr int sg_slot_bytes() {
   return 8 * NB * sg_plane_bytes<CW>() + 2 * sg_ye_bytes<CW>();
 }
-// J V leaves through shared memory too: every consumer warp stages its 8-point x 8 NB-column piece of a grid row
-// ([column][8 points], 64 bytes per column) in one of two private buffers and hands it to the TMA unit
-// (cp.async.bulk.tensor store); columns >= k and points >= m are clipped by the tensor map.
-template <int NB> __host__ __device__ constexpr int sg_out_bytes() { return 8 * NB * 64; }
 template <int NB, int CW> __host__ __device__ constexpr int sg_nslot() {
-  return ((200 * 1024 - 2 * CW * sg_out_bytes<NB>()) / sg_slot_bytes<NB, CW>()) < 16
-             ? ((200 * 1024 - 2 * CW * sg_out_bytes<NB>()) / sg_slot_bytes<NB, CW>())
-             : 16;
+  return (200 * 1024 / sg_slot_bytes<NB, CW>()) < 16 ? (200 * 1024 / sg_slot_bytes<NB, CW>()) : 16;
 }
 template <int NB, int CW> __host__ __device__ constexpr int sg_dyn_bytes() {
-  return sg_slot_bytes<NB, CW>() * sg_nslot<NB, CW>() + 2 * CW * sg_out_bytes<NB>();
+  return sg_slot_bytes<NB, CW>() * sg_nslot<NB, CW>();
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -840,14 +834,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                "l"(tm), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, uint32_t src) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0),
-               "r"(c1), "r"(c2), "r"(src)
-               : "memory");
-}
-__device__ __forceinline__ void sts2(uint32_t a, double2 v) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
-}
 __device__ __forceinline__ double2 lds2(uint32_t a) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
@@ -862,8 +848,8 @@ __device__ __forceinline__ double lds1(uint32_t a) {
 template <int NB, int CW>
 __global__ void __launch_bounds__(32 * (CW + 1), 1)
     stencil_gram_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmY,
-                        const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmJ, StencilPanel p,
-                        int TI, double* __restrict__ partials, unsigned int* ticket, double* __restrict__ Gout) {
+                        const __grid_constant__ CUtensorMap tmE, StencilPanel p, int TI, double* __restrict__ JV,
+                        double* __restrict__ partials, unsigned int* ticket, double* __restrict__ Gout) {
   constexpr int NBLK = nblocks(NB);
   constexpr int SB = sg_slot_bytes<NB, CW>();
   constexpr int NS = sg_nslot<NB, CW>();
@@ -933,10 +919,6 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
     const double wsel = lastkind == 0 ? 1.0 : 0.0, wone = lastkind == 1 ? 1.0 : 0.0;
     const double cuL = wsel * cu, clL = wsel * cl, cdL = wsel * cd;
     const uint32_t eoff = (uint32_t)(8 * NB * PB + YE + 8 * (4 + 8 * warp + 2 * t));
-    // this warp's two output staging buffers and this lane's place in them: column 8 I + g, points 2t, 2t + 1
-    const uint32_t out0 = ring0 + NS * SB + (uint32_t)(2 * warp) * sg_out_bytes<NB>();
-    const uint32_t olane = (uint32_t)(g * 64 + t * 16);
-    uint32_t obuf = 0;
     // ring position: slot index and phase advance together (no modulo in the loop)
     uint32_t slot = 0, phase = 0;
     auto advance = [&]() {
@@ -957,7 +939,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
       advance();
     };
     auto row_step = [&](double2 (&up)[NB], double2 (&mid)[NB], double2 (&dn)[NB], uint32_t& mid_base,
-                        uint32_t& mid_slot, int jseg, int i) {
+                        uint32_t& mid_slot, double* const (&jp)[NB], int64_t ro) {
       mbar_wait(full0 + 8 * slot, phase);
       const uint32_t base = ring0 + slot * SB;
 #pragma unroll
@@ -976,10 +958,6 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
       mid_slot = slot;
       advance();
       const double dga = sg * __dadd_rn(d0, __dmul_rn(p.lam, e.x)), dgb = sg * __dadd_rn(d0, __dmul_rn(p.lam, e.y));
-      // the staging buffer about to be overwritten was handed to the TMA unit two rows ago: its read must be over
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      __syncwarp();
-      const uint32_t ob0 = out0 + obuf * sg_out_bytes<NB>();
       const double dgaL = fma(wsel, dga, wone), dgbL = fma(wsel, dgb, wone);
       double2 tile[NB];
 #pragma unroll
@@ -990,15 +968,10 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
         const double ob = apply_refbits(last ? cuL : cu, last ? clL : cl, last ? dgbL : dgb, last ? cdL : cd, up[I].y,
                                         mid[I].x, mid[I].y, rt[I], dn[I].y);
         tile[I] = make_double2(oa, ob);
-        sts2(ob0 + I * 512 + olane, tile[I]);  // columns >= k are clipped by the store's tensor map
+        // J V goes out with plain 128-bit streaming stores (a quad writes 64 contiguous bytes of a column); staging it in
+        // shared memory for cp.async.bulk.tensor stores was built and measured SLOWER in situ (46.2 vs 41.0 ms per solve)
+        if (!last || lastkind == 0) __stcs(reinterpret_cast<double2*>(jp[I] + ro), tile[I]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_3d(&tmJ, jseg, i, 0, ob0);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      obuf ^= 1u;
 #pragma unroll
       for (int I = 0; I < NB; ++I)
 #pragma unroll
@@ -1031,15 +1004,22 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
         for (int I = 0; I < NB; ++I) rb[I] = lds2(mid_base + poff[I]);
         advance();
       }
-      const int jseg = tj * TJ + 8 * warp;  // first grid point of this warp's segment
+      const int j = tj * TJ + 8 * warp + 2 * t;
+      double* jp[NB];  // this lane's J V columns at (row 0, j); ro = i * m advances with the rows
+#pragma unroll
+      for (int I = 0; I < NB; ++I) jp[I] = JV + (int64_t)(8 * I + g) * p.ldjv + j;
+      int64_t ro = (int64_t)i0 * m;
       int i = i0;
       if (active) {
         while (true) {  // three rows per trip, the window rotating through (ra, rb, rc)
-          row_step(ra, rb, rc, mid_base, mid_slot, jseg, i);
+          row_step(ra, rb, rc, mid_base, mid_slot, jp, ro);
+          ro += m;
           if (++i == i1) break;
-          row_step(rb, rc, ra, mid_base, mid_slot, jseg, i);
+          row_step(rb, rc, ra, mid_base, mid_slot, jp, ro);
+          ro += m;
           if (++i == i1) break;
-          row_step(rc, ra, rb, mid_base, mid_slot, jseg, i);
+          row_step(rc, ra, rb, mid_base, mid_slot, jp, ro);
+          ro += m;
           if (++i == i1) break;
         }
       } else {
@@ -1048,9 +1028,6 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);  // row i1 was only ever a dn row
     }
-    // the J V stores still in flight read this CTA's shared memory: they must have completed before the CTA retires
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    __syncwarp();
   }
   reduce_gram<NBLK, CW, NT>(acc, red, partials, ticket, Gout);
 }
@@ -1117,9 +1094,6 @@ int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, 
   if (int rc = make_column_map(&tmY, d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
   const bool has_e = prm->lam != 0.0;
   if (int rc = make_column_map(&tmE, has_e ? d_expu : d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
-  // J V: k columns of `rows` owned grid rows; the store box is one warp's piece {8 points, 1 row, 8 NB columns}
-  CUtensorMap tmJ;
-  if (int rc = make_column_map(&tmJ, d_JV, lay->m, lay->rows, ldjv, k, 8 * NB, 8, /*force_3d=*/true)) return rc;
   auto kern = stencil_gram_kernel<NB, CW>;
   constexpr int dyn = sg_dyn_bytes<NB, CW>();
   static bool attr_set[64] = {false};
@@ -1133,7 +1107,7 @@ int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, 
   const int64_t ntask = (int64_t)ntj * ceil_div(lay->rows, TI);
   const int ctas = (int)(ntask < ctx->sm_count ? ntask : ctx->sm_count);
   StencilPanel p{lay->m, lay->rows, k, has_e ? 1 : 0, ldjv, prm->c_lap, prm->c_adv, prm->lam, sign};
-  kern<<<ctas, 32 * (CW + 1), dyn, st>>>(tmV, tmY, tmE, tmJ, p, TI, base + CQ_PART, ctx->d_tickets + TK_CHOLQR,
+  kern<<<ctas, 32 * (CW + 1), dyn, st>>>(tmV, tmY, tmE, p, TI, d_JV, base + CQ_PART, ctx->d_tickets + TK_CHOLQR,
                                         base + CQ_LOCAL);
   GNK_LAUNCH_CHECK(ctx);
   return cholqr_tail<NB, RU>(ctx, d_JV, ldjv, lay->n_own, k, d_r + lay->off, sign_a, d_out, st);
@@ -1170,13 +1144,16 @@ extern "C" int gnk_stencil_gram_ls(gnk_ctx* ctx, const gnk_layout* lay, const gn
   static const int cholqr_on = getenv("GNK_LS_CHOLQR") ? atoi(getenv("GNK_LS_CHOLQR")) : 1;
   static const int cholqr_min = getenv("GNK_LS_CHOLQR_MIN") ? atoi(getenv("GNK_LS_CHOLQR_MIN")) : 3;
   static const int fused_on = getenv("GNK_LS_FUSED") ? atoi(getenv("GNK_LS_FUSED")) : 1;
+  // narrowest panel that takes the fused kernel: with one column block the per-row ring hand-over outweighs the saved
+  // pass (k = 2: 0.54 ms fused against 0.33 ms for the two kernels; break-even at k = 6..7, measured at 4096^2)
+  static const int fused_min = getenv("GNK_LS_FUSED_MIN") ? atoi(getenv("GNK_LS_FUSED_MIN")) : 8;
   const int c = k + 1;
   const bool aligned = (lay->m % 8 == 0) && (ldv % 2 == 0) && (ldjv % 2 == 0) && (lay->ld % 2 == 0) &&
                        ((uintptr_t)d_V % 16 == 0) && ((uintptr_t)d_r % 16 == 0) && ((uintptr_t)d_JV % 16 == 0) &&
                        (d_expu == nullptr || (uintptr_t)d_expu % 16 == 0);
   if (!(fused_on && cholqr_on && ctx->ls_method != 1 && (sign == 1.0 || sign == -1.0) &&
         (sign_a == 1.0 || sign_a == -1.0) && aligned && lay->n_own >= 16384 && c <= 32 && c >= cholqr_min &&
-        encode_tiled_fn() != nullptr))
+        c >= fused_min && encode_tiled_fn() != nullptr))
     return 1;
   if (c <= 8) return run_stencil_gram<1, 4>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a, d_out, st);
   if (c <= 16) return run_stencil_gram<2, 2>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a, d_out, st);

@@ -129,6 +129,71 @@ __global__ void __launch_bounds__(TPB) normalize_kernel(const double* __restrict
   }
 }
 
+// normalize fused with the halo exchange of the column it writes (multi-GPU, peer mailboxes attached): the CTAs that
+// write the first / last `cnt` owned doubles also store them into the lower / upper neighbour's mailbox (plain stores
+// over NVLink); the CTA that arrives last -- every store of this rank is then fenced -- raises this rank's flag in both
+// neighbours' mailboxes, waits for theirs, and copies the two received pieces into the halo rows of `out`.  Same
+// protocol, slots and sequence numbers as p2p_halo_kernel (comm.cu); one kernel and one launch gap fewer per outer
+// iteration.  On a breakdown nothing is written but the flags are still exchanged, so the sequence stays in step.
+struct HaloPush {
+  void* const* peers;
+  int rank, nranks, has_lo, has_hi;
+  int64_t off, rows_m, cnt;  // first owned double, owned doubles, doubles per message (depth * m)
+  unsigned long long seq;
+};
+__global__ void __launch_bounds__(TPB) normalize_halo_kernel(const double* __restrict__ x, int64_t len,
+                                                              const double* __restrict__ stats, double atol,
+                                                              double* __restrict__ out, int32_t* flag, HaloPush hp,
+                                                              unsigned int* ticket) {
+  const double ss = stats[0], mx = stats[1];
+  const bool bad = (mx <= atol);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *flag = bad ? 1 : 0;
+  const int parity = (int)(hp.seq & 1ull);
+  if (!bad) {
+    const double nrm = sqrt(ss);
+    double* lo_dst = hp.has_lo ? reinterpret_cast<double*>(static_cast<char*>(hp.peers[hp.rank - 1]) +
+                                                            p2p_halo_off(hp.nranks, parity, 1))
+                               : nullptr;
+    double* hi_dst = hp.has_hi ? reinterpret_cast<double*>(static_cast<char*>(hp.peers[hp.rank + 1]) +
+                                                            p2p_halo_off(hp.nranks, parity, 0))
+                               : nullptr;
+    const int64_t lo_end = hp.off + hp.cnt, hi_beg = hp.off + hp.rows_m - hp.cnt, hi_end = hp.off + hp.rows_m;
+    const int64_t nv = len >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+      double2 v = ld2(x + 2 * i);
+      v.x = v.x / nrm;
+      v.y = v.y / nrm;
+      st2(out + 2 * i, v);
+      const int64_t e = 2 * i;  // off, cnt and rows_m are even: a pair never straddles a piece
+      if (lo_dst && e >= hp.off && e < lo_end) st2(lo_dst + (e - hp.off), v);
+      if (hi_dst && e >= hi_beg && e < hi_end) st2(hi_dst + (e - hi_beg), v);
+    }
+    __threadfence_system();  // this thread's remote stores are visible before the CTA takes its ticket
+  }
+  if (!grid_arrive_last(ticket)) return;
+  char* mine = static_cast<char*>(hp.peers[hp.rank]);
+  const unsigned long long* myflags = reinterpret_cast<const unsigned long long*>(mine + 1024);
+  if (threadIdx.x == 0 && hp.has_lo) {
+    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(hp.peers[hp.rank - 1]) + 1024) + 1, hp.seq);
+    wait_flag(myflags + 0, hp.seq);
+  }
+  if (threadIdx.x == 32 && hp.has_hi) {
+    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(hp.peers[hp.rank + 1]) + 1024) + 0, hp.seq);
+    wait_flag(myflags + 1, hp.seq);
+  }
+  __syncthreads();
+  if (bad) return;
+  if (hp.has_lo) {
+    const double* g = reinterpret_cast<const double*>(mine + p2p_halo_off(hp.nranks, parity, 0));
+    for (int64_t i = threadIdx.x; i < hp.cnt; i += blockDim.x) out[hp.off - hp.cnt + i] = ld_volatile(g + i);
+  }
+  if (hp.has_hi) {
+    const double* g = reinterpret_cast<const double*>(mine + p2p_halo_off(hp.nranks, parity, 1));
+    for (int64_t i = threadIdx.x; i < hp.cnt; i += blockDim.x) out[hp.off + hp.rows_m + i] = ld_volatile(g + i);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // h[j] = sum_i V[j*ld + i] * w[i], i in [0, n) (pointers already offset to the owned part)
 constexpr int JB = 8;  // columns per pass: 8 accumulators keep the kernel at ~64 registers -> 32+ warps per SM
@@ -358,6 +423,30 @@ int gnk_normalize(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, const 
   GNK_REQUIRE((lay->ld & 1) == 0, "gnk_normalize: ld must be even");
   int grid = stream_grid(ctx, lay->ld / 2, 8);
   normalize_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_x, lay->ld, d_stats, atol, d_out, d_flag);
+  GNK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gnk_comm_halo_exchange(gnk_ctx* ctx, const gnk_layout* lay, double* d_col, int depth, void* stream);
+
+int gnk_normalize_halo(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, const double* d_stats, double atol,
+                       double* d_out, int32_t* d_flag, void* stream) {
+  GNK_REQUIRE(ctx && lay && d_x && d_stats && d_out && d_flag, "gnk_normalize_halo: null argument");
+  const int depth = lay->halo;
+  const int64_t cnt = (int64_t)depth * lay->m;
+  const bool fused = ctx->nranks > 1 && ctx->p2p_ready && ctx->p2p_fused && lay->m > 0 && depth >= 1 &&
+                     depth <= lay->rows && cnt <= P2P_HMAX && (lay->ld & 1) == 0 && (lay->off & 1) == 0 &&
+                     (cnt & 1) == 0 && (lay->n_own & 1) == 0;
+  if (!fused) {
+    if (int rc = gnk_normalize(ctx, lay, d_x, d_stats, atol, d_out, d_flag, stream)) return rc;
+    if (ctx->nranks > 1 && lay->m > 0) return gnk_comm_halo_exchange(ctx, lay, d_out, depth, stream);
+    return 0;
+  }
+  HaloPush hp{ctx->d_p2p_peer, ctx->rank, ctx->nranks, lay->has_lo, lay->has_hi, lay->off, lay->n_own, cnt,
+              ++ctx->p2p_hseq};
+  int grid = stream_grid(ctx, lay->ld / 2, 8);
+  normalize_halo_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_x, lay->ld, d_stats, atol, d_out, d_flag, hp,
+                                                                ctx->d_tickets + TK_NORMALIZE);
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -131,14 +131,17 @@ class GeneralizedKrylowSubspace:
         if not rt.fused_reductions:
             rt.allreduce(self.stats, 2, 2)
         new = self.col(self.k)
+        fp = ptr(self.flag) if flag_ptr is None else flag_ptr
         with rt.mark("normalize", 16.0 * n):
-            _lib.check(lib.gnk_normalize(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8, ptr(new),
-                                         ptr(self.flag) if flag_ptr is None else flag_ptr, rt.stream),
-                       "gnk_normalize")
-        if halo_exchange is not None:
-            # a breakdown leaves column k unwritten; exchanging its halo rows anyway is harmless (the column is not
-            # part of the basis then) and keeps every rank in the same sequence of collectives
-            halo_exchange(self.V, 2, self.k * self.ld)
+            if halo_exchange is not None:
+                # the one halo exchange of an outer iteration rides in the normalisation kernel (border CTAs store into
+                # the neighbours' mailboxes).  A breakdown leaves column k unwritten; the flags are exchanged anyway,
+                # which keeps every rank in the same sequence of collectives
+                _lib.check(lib.gnk_normalize_halo(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8,
+                                                  ptr(new), fp, rt.stream), "gnk_normalize_halo")
+            else:
+                _lib.check(lib.gnk_normalize(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8, ptr(new),
+                                             fp, rt.stream), "gnk_normalize")
 
     def commit(self):
         """make the column written by the last ``dev_expand_enqueue`` part of the basis"""

@@ -106,6 +106,13 @@ int gnk_norm_stats(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, doubl
  * x0 == 0, krylow.py:31-34); otherwise *d_flag = 0. */
 int gnk_normalize(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, const double* d_stats,
                   double atol, double* d_out, int32_t* d_flag, void* stream);
+/* gnk_normalize followed by the exchange of the new column's `halo` rows with the neighbouring ranks (the one halo
+ * exchange of an outer iteration: every other vector inherits valid halos from the basis).  With
+ * the peer mailboxes attached both happen in ONE kernel: the CTAs that write the first / last owned rows also store
+ * them into the neighbours' mailboxes over NVLink, and the CTA that arrives last exchanges the flags and fills this
+ * rank's halo rows.  Single rank / no mailboxes: gnk_normalize (+ gnk_comm_halo_exchange). */
+int gnk_normalize_halo(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, const double* d_stats, double atol,
+                       double* d_out, int32_t* d_flag, void* stream);
 /* h = V_k^T w over owned entries (first half of krylow.py:64). */
 int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, const double* d_w,
                  double* d_h, void* stream);

@@ -285,6 +285,13 @@ class MockLib:
         arr(out, 1)[0] = np.dot(arr(x, n), arr(y, n))
         return 0
 
+    def gnk_normalize_halo(self, ctx, lay, x, stats, atol, out, flag, stream):
+        rc = self.gnk_normalize(ctx, lay, x, stats, atol, out, flag, stream)
+        lo = obj(lay)
+        if rc == 0 and self.world > 1 and lo.m > 0:
+            return self.gnk_comm_halo_exchange(ctx, lay, out, lo.halo, stream)
+        return rc
+
     def gnk_stencil_gram_ls(self, *a):
         return 1  # "not eligible": the host falls back to gnk_stencil_apply + gnk_tsqr_ls (which the mock implements)
 
