@@ -62,6 +62,7 @@ SIGNATURES = {
     "gnk_tsqr_ls": (_I, [_P, _P, _L, _L, _I, _P, _D, _P, _P]),
     "gnk_stencil_gram_ls": (_I, [_P, _LP, _BP, _P, _P, _L, _I, _I, _P, _D, _P, _L, _D, _P, _P]),
     "gnk_tsqr_ls_method": (_I, [_P, _I]),
+    "gnk_gram_cgls": (_I, [_P, _P, _L, _L, _I, _P, _D, _D, _P, _P]),
     "gnk_spmm_csr": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _I, _D, _P, _L, _L, _P]),
     "gnk_csr_row_sumsq": (_I, [_P, _L, _P, _P, _P, _P]),
     "gnk_axpby": (_I, [_P, _L, _D, _P, _D, _P, _P, _P]),

@@ -54,6 +54,7 @@ int gnk_destroy(gnk_ctx* ctx) {
   if (ctx->d_gather) cudaFree(ctx->d_gather);
   if (ctx->d_apart) cudaFree(ctx->d_apart);
   if (ctx->d_cholqr) cudaFree(ctx->d_cholqr);
+  if (ctx->d_gramw) cudaFree(ctx->d_gramw);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
   return 0;

@@ -41,6 +41,7 @@ struct gnk_ctx {
   size_t apart_bytes = 0;
   // CholeskyQR2 scratch (cholqr.cu): per-CTA Gram partials, the gathered Gram matrices, T, R1, status word
   double* d_cholqr = nullptr;
+  double* d_gramw = nullptr;          // wide Gram matrix scratch of gnk_gram_cgls (gram_cgls.cu)
   int ls_method = 0;                  // gnk_tsqr_ls_method: 0 automatic, 1 Householder TSQR only
 };
 
@@ -58,7 +59,7 @@ constexpr int64_t PART_RESID = GNK_PARTIALS - 65536;                // residual 
 static_assert(PART_SCAL + 64 <= PART_RESID, "partials scratch overflow");
 
 enum TicketSlot { TK_RESID = 0, TK_STATS = 1, TK_DOTS = 2, TK_UPDATE = 3, TK_DOT1 = 4, TK_CG = 5, TK_APPLY_DOTS = 6,
-                  TK_CHOLQR = 7, TK_NORMALIZE = 8 };
+                  TK_CHOLQR = 7, TK_NORMALIZE = 8, TK_GRAMW = 9 };
 
 void gnk_set_error(const std::string& s);
 int gnk_fail(const char* what, cudaError_t e, const char* file, int line);

@@ -346,7 +346,15 @@ def gauss_newton_krylow(
                 with rt.mark("tsqr", 8.0 * n_res_own * (k + 1)):
                     tsqr_solve(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, blk, method=ls_method)
             elif ls_solver == "cgls":
-                cgls_dense(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, cg_rtol, blk)
+                # CG on the k x k normal equations formed once on the tensor pipe, recurrence in one kernel
+                # (gnk_gram_cgls); panels it does not take (odd row counts, > 55 columns) run the reference-shaped loop
+                # over the n x k panel (cgls_dense)
+                if k + 1 <= 56 and n_res_own % 2 == 0 and ldjv % 2 == 0:
+                    with rt.mark("gram_cgls", 8.0 * n_res_own * (k + 1)):
+                        _lib.check(lib.gnk_gram_cgls(rt.ctx, ptr(JV), ldjv, n_res_own, k, ptr(F_cur, res_off), -1.0,
+                                                     float(cg_rtol), ptr(blk), rt.stream), "gnk_gram_cgls")
+                else:
+                    cgls_dense(rt, JV, ldjv, n_res_own, k, F_cur[res_off:], -1.0, cg_rtol, blk)
             else:
                 raise ValueError("ls_solver must be 'qr' or 'cgls'")
             # Speculative basis expansion: everything the expansion needs -- J at the trial point (e^x is a by-product

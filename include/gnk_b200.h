@@ -206,6 +206,17 @@ int gnk_cgls(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, double rtol, 
 int gnk_cgls_x0(gnk_ctx* ctx, const gnk_linop* op, const double* d_y, const double* d_x0, double rtol,
                 int preconditioner, double* d_x, double* d_work, int64_t* iters, void* stream);
 
+/* The projected least squares of GNK solved by CGLS (BASELINE config 5, "Krylov dim 50 with CGLS inner solve"):
+ * cg_least_squares(sign_a * A, y, cg_rtol = rtol, preconditioner = True) of gauss_newton.py:11-60 for the DENSE n_rows x k
+ * panel A (column-major, stride lda, k <= 55).  scipy's cg touches A through p -> A^T (A p) (16 n k bytes per CG iteration);
+ * here G = A^T A, A^T y and y^T y are formed once (one sweep over the panel on the FP64 tensor pipe, up to 7 column
+ * blocks) and the whole recurrence -- x0 = 0, M = 1 / diag(A^T A), stop when |r| < rtol |A^T y| tested at the top of
+ * each iteration, at most 10 k iterations -- runs in one single-CTA kernel on the k x k system.  Result block as
+ * gnk_tsqr_ls (d, d^T G d = ||A d||^2, ||y - A d||^2, 0, ||d||^2, sqrt(diag G)); d_out[2k+4] = CG iterations taken.
+ * With a communicator attached the ranks' Gram matrices are summed in rank order before the iteration. */
+int gnk_gram_cgls(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k, const double* d_y,
+                  double sign_a, double rtol, double* d_out, void* stream);
+
 /* ---- chained Rosenbrock problem on the device (rosenbrock_problem.py:8-19) -------------- */
 /* F = sqrt2 * [10 (x[1:] - x[:-1]^2) ; 1 - x[:-1]]  (2p-2 values), numpy's rounding order (res, :8-12). */
 int gnk_rosenbrock_residual(gnk_ctx* ctx, int64_t p, double sqrt2, const double* d_x, double* d_F, void* stream);

@@ -273,14 +273,14 @@ def cgx0():
     print("cg_x0.npz written:", {k: int(v) for k, v in flat.items() if "/it_" in k})
 
 
-def sensitivity(G, name, runs_kw):
+def sensitivity(G, name, runs_kw, seed=7):
     """The reference against ITSELF when the start vector u0 is perturbed by one unit in the last place (relative
     2^-52, random signs, seed 7).  The deviation of the perturbed trace from the unperturbed one is the conditioning of
     the reference's trajectory: no independent implementation (different summation order, FMA contraction, another
     exp) can be expected to reproduce the iterates more closely than a small multiple of this envelope.  (Perturbing y
     instead under-estimates it: |y| << |res(u0)| on these noise-dominated starts.)"""
     pb, y, res, jac, err, u0 = bratu_setup(G, 5, 10)
-    sgn = np.random.RandomState(7).choice([-1.0, 1.0], size=u0.shape[0])
+    sgn = np.random.RandomState(seed).choice([-1.0, 1.0], size=u0.shape[0])
     u0p = u0 * (1.0 + sgn * 2.0 ** -52)
     out = {}
     for rname, kw in runs_kw.items():
@@ -302,7 +302,21 @@ def sens4097():
     sensitivity(4097, "bratu_g4097_sens", dict(gnk_k30=dict(max_iter=31)))
 
 
+def sens4097b():
+    """two more draws of the 1-ulp perturbation (other random sign patterns): one draw is ONE sample of the reference's
+    conditioning; the parity bound uses the largest of the three envelopes per iteration"""
+    sensitivity(4097, "bratu_g4097_sens2", dict(gnk_k30=dict(max_iter=31)), seed=8)
+    sensitivity(4097, "bratu_g4097_sens3", dict(gnk_k30=dict(max_iter=31)), seed=9)
+
+
+def sens1025b():
+    sensitivity(1025, "bratu_g1025_sens2", dict(gnk_k30=dict(max_iter=31),
+                                                gnk_restart30=dict(max_iter=100, krylow_restart=30)), seed=8)
+    sensitivity(1025, "bratu_g1025_sens3", dict(gnk_k30=dict(max_iter=31),
+                                                gnk_restart30=dict(max_iter=100, krylow_restart=30)), seed=9)
+
+
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["small"]:
         dict(small=small, g1025=g1025, g4097=g4097, kernels=kernels_fixture, sens101=sens101, sens1025=sens1025,
-             sens4097=sens4097, ttt=ttt, cgx0=cgx0)[what]()
+             sens4097=sens4097, sens4097b=sens4097b, sens1025b=sens1025b, ttt=ttt, cgx0=cgx0)[what]()

@@ -292,6 +292,27 @@ class MockLib:
             return self.gnk_comm_halo_exchange(ctx, lay, out, lo.halo, stream)
         return rc
 
+    def gnk_gram_cgls(self, ctx, A, lda, n_rows, k, y, sign_a, rtol, out, stream):
+        """CG on the explicit normal equations, as the device kernel does (Gram matrices summed over the ranks)"""
+        from oracle.gnk_oracle import pcg
+        self.launches += 1
+        Am = arr(A, lda * k).reshape(k, lda)[:, :n_rows].T * sign_a
+        yv = arr(y, n_rows)
+        G, b, yy = Am.T @ Am, Am.T @ yv, np.array([yv @ yv])
+        if self.world > 1:
+            packed = self._allgather(np.concatenate([G.reshape(-1), b, yy])).reshape(self.world, -1).sum(axis=0)
+            G, b, yy = packed[:k * k].reshape(k, k), packed[k * k:k * k + k], packed[-1:]
+        d, its = pcg(lambda v: G @ v, b, 1.0 / np.diag(G), rtol, maxiter=10 * k)
+        o = arr(out, 2 * k + 5)
+        o[:k] = d
+        o[k] = d @ G @ d
+        o[k + 1] = yy[0] - 2 * d @ b + d @ G @ d
+        o[k + 2] = 0.0
+        o[k + 3] = d @ d
+        o[k + 4:2 * k + 4] = np.sqrt(np.diag(G))
+        o[2 * k + 4] = its
+        return 0
+
     def gnk_stencil_gram_ls(self, *a):
         return 1  # "not eligible": the host falls back to gnk_stencil_apply + gnk_tsqr_ls (which the mock implements)
 

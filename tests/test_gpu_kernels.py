@@ -467,6 +467,40 @@ def test_cgls_with_initial_guess_matches_reference_golden(g, precond):
     assert it == 0 and np.array_equal(x, xs)
 
 
+@pytest.mark.parametrize("n,k", [(4096, 3), (20000, 15), (30002, 31), (16384, 32), (40000, 40), (65536, 50), (20480, 55)])
+def test_gram_cgls_matches_the_reference_cg_least_squares(g, n, k):
+    """gnk_gram_cgls (Gram matrix on the tensor pipe + the CG recurrence in one kernel on the k x k system) against the
+    oracle's restatement of cg_least_squares(A, y, cg_rtol, preconditioner=True) (gauss_newton.py:11-60 / scipy cg)
+    applied to the dense panel: same iteration count (+-1: the stopping test is evaluated on differently rounded
+    residuals), same solution to the accuracy of the stopping rule, ||A d||^2 and ||y - A d||^2 consistent with d."""
+    _lib, device = _lib_mods()
+    rt = g.get_runtime()
+    rs = np.random.RandomState(n + k)
+    A = rs.normal(size=(n, k)) @ (np.eye(k) + 0.2 * rs.normal(size=(k, k)))
+    A *= np.exp(rs.uniform(-2, 2, size=k))[None, :]
+    y = rs.normal(size=n)
+    lda = (n + 15) // 16 * 16
+    dA = rt.zeros(lda * k)
+    for j in range(k):
+        rt.upload(np.ascontiguousarray(A[:, j]), dA[j * lda:j * lda + n])
+    dy = rt.zeros(lda)
+    rt.upload(y, dy[:n])
+    for sign in (1.0, -1.0):
+        for rtol in (1e-4, 1e-10):
+            out = rt.zeros(256)
+            _lib.check(rt.lib.gnk_gram_cgls(rt.ctx, device.ptr(dA), lda, n, k, device.ptr(dy), sign, rtol, device.ptr(out),
+                                            rt.stream), "gnk_gram_cgls")
+            v = rt.read(out, 2 * k + 5).copy()
+            xr, itr = orc.cgls(sign * A, y, rtol=rtol, preconditioner=True)
+            d = v[:k]
+            assert abs(int(v[2 * k + 4]) - itr) <= 1, (int(v[2 * k + 4]), itr)
+            assert rel(d, xr) < max(50 * rtol, 1e-9), (rel(d, xr), rtol)
+            Ad = sign * A @ d
+            assert abs(v[k] - Ad @ Ad) <= 1e-10 * (Ad @ Ad) and abs(v[k + 3] - d @ d) <= 1e-12 * (d @ d)
+            assert abs(v[k + 1] - np.sum((y - Ad) ** 2)) <= 1e-9 * (y @ y)
+            assert np.allclose(v[k + 4:2 * k + 4], np.linalg.norm(A, axis=0), rtol=1e-12)
+
+
 # ------------------------------------------------------------------------------------------------
 # public building blocks with the reference's signatures
 # ------------------------------------------------------------------------------------------------
