@@ -379,11 +379,11 @@ class Harness:
     # --------------------------------------------------------------------------------------------
     def parity(self, pb, res, jac, x0_dev, y, kw, spec):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from golden_util import Golden, sensitivity_bound
+        from golden_util import Golden, bound_for
         gname, rname, sname = spec["golden"]
         try:
             gr = Golden(gname).run(rname)
-            gs = Golden(sname).run(rname)
+            full_bound = bound_for(gname, rname)
         except Exception as e:
             return dict(available=False, why=f"golden fixture missing: {e}")
         idx = gr["sample_idx"]
@@ -400,7 +400,7 @@ class Harness:
         X = np.array(xs[:ncmp])
         scale = np.max(np.abs(gr["xs"][:ncmp]), axis=1, keepdims=True)
         dev = np.max(np.abs(X - gr["xs"][:ncmp]) / scale, axis=1)
-        bound = sensitivity_bound(gr, gs)[:ncmp]
+        bound = full_bound[:ncmp]
         loss = res.loss(out.x)
         gl = float(gr["loss"][-1]) if np.isfinite(gr["loss"][-1]) else None
         restart = spec["restart"]
@@ -414,7 +414,9 @@ class Harness:
                  max_dev_over_bound=float(np.max(dev / bound)), within_bound=bool(np.all(dev <= bound)),
                  dev_per_iteration=[float(f"{v:.3e}") for v in dev],
                  bound_per_iteration=[float(f"{v:.3e}") for v in bound],
-                 bound="per iteration max(1e-10, 30 x the reference's own 1-ulp envelope) (tests/golden_util.py)",
+                 bound="per iteration max(1e-10, 30 x the reference's own envelope under a 1-ulp change of u0, 3 x its "
+                       "envelope under a 1-ulp change of its projected least-squares solutions) "
+                       "(tests/golden_util.py:sensitivity_bound; fixtures by oracle/gen_golden.py)",
                  final_loss=float(loss), golden_final_loss=gl,
                  final_loss_dev=None if gl is None else float(abs(loss - gl) / gl))
         return p

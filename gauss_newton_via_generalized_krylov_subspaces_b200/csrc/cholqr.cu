@@ -489,6 +489,7 @@ __global__ void __launch_bounds__(FT) cholqr_factor1_kernel(const double* __rest
   }
   double a = gather_gram(parts, nparts, NB, c, nblocks(NB) * 64);
   if (l == k && i < k) a *= sign;  // (sign A)^T y
+  if (l == k && i < k) aux[1 + i] = a;  // b = (sign A)^T y for the finishing kernel: ||A d||^2 = b^T d at the solution
   double r, min_ratio;
   const bool ok = block_cholesky(a, c, PIVOT_FLOOR_1, rowbuf, diag, r, min_ratio);
   if (threadIdx.x == 0) *status = ok ? ((method != 2 && min_ratio >= REFINE_FLOOR) ? 0 : 2) : 1;
@@ -578,6 +579,11 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
       const double rii = row ? R1g[l * MAXC + l] : 1.0;
       const double d2 = warp_sum(d * d), dl2 = warp_sum(dl * dl);
       const double ndef = warp_sum((row && fabs(rii) <= 1e-8) ? 1.0 : 0.0);
+      // ||A d||^2 for the Armijo rule (armijo_goldstein.py:50).  At the least-squares solution A^T A d = A^T y, so
+      // ||A d||^2 = b^T d with b = (sign A)^T y straight from the Gram pass: no conditioning enters (the error is
+      // second order in the remaining gradient), unlike ||A d0||^2 = |R1^{-T} b|^2 of the unrefined solution, which is
+      // only good to cond^2 eps ~ 1e-7.
+      const double bd = warp_sum(row ? aux[1 + l] * d : 0.0);
       if (l == 0) {
         dsum[0] = d2;
         dsum[1] = dl2;
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
           out[k + 4 + l] = rii;
         }
         if (l == 0) {
-          out[k] = aux[0];
+          out[k] = bd;
           out[k + 1] = gs[k];
           out[k + 2] = ndef;
           out[k + 3] = d2;
@@ -660,8 +666,8 @@ constexpr int64_t CQ_ALL2 = CQ_LOCAL2 + NE2_MAX;
 constexpr int64_t CQ_T = CQ_ALL2 + P2P_MAXR * NE2_MAX;             // T (MAXC x TLD)
 constexpr int64_t CQ_R1 = CQ_T + MAXC * TLD;                       // R1 (MAXC x MAXC)
 constexpr int64_t CQ_D0 = CQ_R1 + MAXC * MAXC;                     // normal-equation solution d0
-constexpr int64_t CQ_AUX = CQ_D0 + MAXC;                           // ||A d0||^2
-constexpr int64_t CQ_STATUS = CQ_AUX + 8;                          // int status word
+constexpr int64_t CQ_AUX = CQ_D0 + MAXC;                           // ||A d0||^2, then b = (sign A)^T y (k doubles)
+constexpr int64_t CQ_STATUS = CQ_AUX + 8 + MAXC;                   // int status word
 constexpr int64_t CQ_TOTAL = CQ_STATUS + 8;
 
 template <int KC>

@@ -131,9 +131,10 @@ int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k
  * Large panels (3 <= k+1 <= 32, >= 16384 rows, even row count, 16-byte aligned, sign_a = +-1) are solved on the FP64
  * tensor pipe instead (cholqr.cu): Gram matrix of the panel by DMMAs + Cholesky, then either one step of iterative
  * refinement of the normal-equation solution (one more HBM-bound pass; chosen on the device when every Cholesky pivot
- * ratio is >= 1e-10, i.e. cond <~ 1e5) or the second pass of CholeskyQR2 (R = R2 R1).  Same result block (diag(R) > 0;
- * in the refinement form d_out[k] = ||A d0||^2 of the normal-equation solution d0, equal to ||A d||^2 to ~1e-7
- * relative, and d_out[k+1] = ||y - A d0||^2).  That path REFUSES panels whose Gram matrix is numerically rank
+ * ratio is >= 1e-10, i.e. cond <~ 1e5) or, on request (gnk_tsqr_ls_method 2), the second pass of CholeskyQR2
+ * (R = R2 R1).  Same result block (diag(R) > 0; in the refinement form d_out[k] = (A^T y)^T d, which equals ||A d||^2 at
+ * the least-squares solution with an error of second order in the remaining gradient, and d_out[k+1] = ||y - A d0||^2
+ * of the normal-equation solution d0).  That path REFUSES panels whose Gram matrix is numerically rank
  * deficient (pivot ratio < 1e-12, e.g. a consistent system) or whose refinement step is not small: it then writes
  * d = 0 and d_out[k+2] = -1, and the caller re-issues the call after gnk_tsqr_ls_method(ctx, 1). */
 int gnk_tsqr_ls(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k,

@@ -288,6 +288,41 @@ def sensitivity(G, name, runs_kw, seed=7):
     save(name, out)
 
 
+def sensitivity_ls(G, name, runs_kw, seed=11):
+    """The reference against ITSELF when every projected least-squares solution it computes
+    (gauss_newton_krylow.py:89) is moved by ONE unit in the last place per component (random signs).  No independent
+    implementation can reproduce the rounding of those k numbers, and the trajectory amplifies it: on the fine grids
+    the first iterate x_1 = (c + d) v_0 is formed by a ~1e7-fold cancellation, so one ulp of d is ~1e-9 of x_1.
+    (Perturbing u0 -- ``sensitivity`` above -- does not show this: the mathematical effect of a random 1-ulp change
+    of 1.7e7 inputs averages out and the rounded d stays the same double.)"""
+    import gauss_newton_krylow as ref_gnk
+    pb, y, res, jac, err, u0 = bratu_setup(G, 5, 10)
+    orig = ref_gnk.linear_least_squares
+    out = {}
+    try:
+        for rname, kw in runs_kw.items():
+            rs = np.random.RandomState(seed)
+
+            def perturbed(A, yy):
+                d = orig(A, yy)
+                return d + rs.choice([-1.0, 1.0], size=d.shape[0]) * np.spacing(np.abs(d))
+
+            ref_gnk.linear_least_squares = perturbed
+            out[rname] = run(gauss_newton_krylow, res, u0, jac, err, loss_every=0, **kw)
+    finally:
+        ref_gnk.linear_least_squares = orig
+    save(name, out)
+
+
+def sensd4097():
+    sensitivity_ls(4097, "bratu_g4097_sensd", dict(gnk_k30=dict(max_iter=31)))
+
+
+def sensd1025():
+    sensitivity_ls(1025, "bratu_g1025_sensd", dict(gnk_k30=dict(max_iter=31),
+                                                   gnk_restart30=dict(max_iter=100, krylow_restart=30)))
+
+
 def sens101():
     sensitivity(101, "bratu_g101_sens", dict(gnk_res_old=dict(max_iter=100),
                                              gnk_restart30=dict(max_iter=100, krylow_restart=30)))
@@ -319,4 +354,5 @@ def sens1025b():
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["small"]:
         dict(small=small, g1025=g1025, g4097=g4097, kernels=kernels_fixture, sens101=sens101, sens1025=sens1025,
-             sens4097=sens4097, sens4097b=sens4097b, sens1025b=sens1025b, ttt=ttt, cgx0=cgx0)[what]()
+             sens4097=sens4097, sens4097b=sens4097b, sens1025b=sens1025b, sensd4097=sensd4097, sensd1025=sensd1025, ttt=ttt,
+             cgx0=cgx0)[what]()

@@ -64,7 +64,7 @@ def main():
     xs = np.array(xs)
     n = len(xs)
     dev = np.max(np.abs(xs - gold["xs"][:n]) / np.max(np.abs(gold["xs"][:n]), axis=1, keepdims=True), axis=1)
-    tol = sensitivity_bound(gold, sens)
+    tol = sensitivity_bound(gold, [sens])
     for i in range(n):
         print(f"iteration {i + 1:3d}  deviation {dev[i]:.2e}  tolerance {tol[i]:.2e}  {'ok' if dev[i] <= tol[i] else 'FAIL'}")
 

@@ -26,7 +26,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     import gauss_newton_via_generalized_krylov_subspaces_b200 as g
-    from golden_util import Golden, Recorder, check_trace, rel, sensitivity_bound
+    from golden_util import Golden, Recorder, bound_for, check_trace, rel
     from oracle import gnk_oracle as orc
 
     rt = g.get_runtime()
@@ -65,7 +65,7 @@ def main():
         print(f"[multi] G=34 world={world}: nit={out.nit} ok", flush=True)
 
     # ---- Bratu 1024^2, k <= 30: golden trace of the reference ----------------------------------------
-    gd, gs = Golden("bratu_g1025"), Golden("bratu_g1025_sens")
+    gd = Golden("bratu_g1025")
     o = orc.BratuOracle(1025, 5, 10)
     y, u0 = o.operator(o.u_true), o.start_vector(seed=42)
     pb = g.BratuPdeProblem(1025, 5, 10)
@@ -73,7 +73,7 @@ def main():
     gr = gd.run("gnk_k30")
     rec = Recorder(gr["sample_idx"], err)
     out = g.gauss_newton_krylow(res, u0, jac, callback=rec, max_iter=31)
-    check_trace(rec, gr, sensitivity_bound(gr, gs.run("gnk_k30")))
+    check_trace(rec, gr, bound_for("bratu_g1025", "gnk_k30"))
     assert (out.nit, out.nrev) == (30, 31) and gather_equal(out.x)
     if rank == 0:
         xs = np.array(rec.xs)
@@ -83,7 +83,7 @@ def main():
     # ---- the north-star workload itself: Bratu 4096^2, k = 1..30, golden trace of the reference --------------------
     # (skipped with GNK_MULTI_SKIP_4096=1 for quick plumbing checks)
     if os.environ.get("GNK_MULTI_SKIP_4096", "0") != "1":
-        gd, gs = Golden("bratu_g4097"), Golden("bratu_g4097_sens")
+        gd = Golden("bratu_g4097")
         o = orc.BratuOracle(4097, 5, 10)
         y, u0 = o.operator(o.u_true), o.start_vector(seed=42)
         pb = g.BratuPdeProblem(4097, 5, 10)
@@ -92,7 +92,7 @@ def main():
         assert np.array_equal(u0[gr["sample_idx"]], gd["u0_sample"]) and np.array_equal(y[gr["sample_idx"]], gd["y_sample"])
         rec = Recorder(gr["sample_idx"], err)
         out = g.gauss_newton_krylow(res, u0, jac, callback=rec, max_iter=31)
-        check_trace(rec, gr, sensitivity_bound(gr, gs.run("gnk_k30")))
+        check_trace(rec, gr, bound_for("bratu_g4097", "gnk_k30"))
         assert (out.nit, out.nrev, out.njev) == (30, 31, 30) and gather_equal(out.x)
         xs = np.array(rec.xs)
         d = np.max(np.abs(xs - gr["xs"]) / np.max(np.abs(gr["xs"]), axis=1, keepdims=True), axis=1)

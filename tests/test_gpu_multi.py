@@ -26,5 +26,11 @@ def test_sharded_cuda_nccl(world):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert p.returncode == 0 and "MULTI_OK" in p.stdout, (p.stdout[-3000:], p.stderr[-3000:])
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    log = os.path.join(ROOT, "gpurun_out", f"multi_worker_w{world}.log")
+    if os.path.isdir(os.path.dirname(log)):
+        with open(log, "w") as f:
+            f.write(p.stdout + "\n==== stderr ====\n" + p.stderr)
+    print(p.stdout[-4000:])
+    print(p.stderr[-6000:])
+    assert p.returncode == 0 and "MULTI_OK" in p.stdout

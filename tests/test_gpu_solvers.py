@@ -15,7 +15,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from golden_util import Golden, Recorder, check_trace, rel, sensitivity_bound  # noqa: E402
+from golden_util import Golden, Recorder, bound_for, check_trace, rel  # noqa: E402
 from oracle import gnk_oracle as orc  # noqa: E402
 
 TOL = 1e-10
@@ -350,12 +350,12 @@ def _large(g, G):
 
 
 def test_bratu_1024(g):
-    gd, gs = Golden("bratu_g1025"), Golden("bratu_g1025_sens")
+    gd = Golden("bratu_g1025")
     pb, res, jac, err, u0, y = _large(g, 1025)
     idx = gd.run("gnk_k30")["sample_idx"]
     assert np.array_equal(u0[idx], gd["u0_sample"]) and np.array_equal(y[idx], gd["y_sample"])  # bit-identical inputs
     gr = gd.run("gnk_k30")
-    bound = sensitivity_bound(gr, gs.run("gnk_k30"))
+    bound = bound_for("bratu_g1025", "gnk_k30")
     out, rec = _run_gnk(g, res, jac, err, u0, gr, max_iter=31, tol=bound)
     tail = Recorder(gr["sample_idx"], None)  # from iteration 5 on the plain 1e-10 bar holds (measured ~1e-12)
     tail.xs, tail.xnorm, tail.nfev = rec.xs[4:], rec.xnorm[4:], rec.nfev[4:]
@@ -363,7 +363,7 @@ def test_bratu_1024(g):
     # restart 30, 99 iterations: iteration-31/61/91 decisions are thin (SURVEY 8c'), counts must still match;
     # after a restart the reference itself moves by 7e-7 under the 1-ulp perturbation
     gr = gd.run("gnk_restart30")
-    bound = sensitivity_bound(gr, gs.run("gnk_restart30"))
+    bound = bound_for("bratu_g1025", "gnk_restart30")
     out, rec = _run_gnk(g, res, jac, err, u0, gr, max_iter=100, restart=30, tol=bound, tol_after=bound)
     # three restarts in: the reference's own 1-ulp envelope is 7e-7 on the iterates by now
     assert abs(rec.err[-1] - gr["err"][-1]) < 1e-6 * gr["err"][-1]
@@ -371,11 +371,11 @@ def test_bratu_1024(g):
 
 def test_bratu_4096_k30(g):
     """north-star workload: Bratu 4096^2 (16.7M unknowns), 30 outer iterations, k = 1..30 (no restart event)."""
-    gd, gs = Golden("bratu_g4097"), Golden("bratu_g4097_sens")
+    gd = Golden("bratu_g4097")
     pb, res, jac, err, u0, y = _large(g, 4097)
     gr = gd.run("gnk_k30")
     assert np.array_equal(u0[gr["sample_idx"]], gd["u0_sample"]) and np.array_equal(y[gr["sample_idx"]], gd["y_sample"])
-    bound = sensitivity_bound(gr, gs.run("gnk_k30"))
+    bound = bound_for("bratu_g4097", "gnk_k30")
     out, rec = _run_gnk(g, res, jac, err, u0, gr, max_iter=31, tol=bound)
     # from iteration 13 on (and at the end) the plain 1e-10 bar, in fact ~1e-13, holds
     check = Recorder(gr["sample_idx"], None)
