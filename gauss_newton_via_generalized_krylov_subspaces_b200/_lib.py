@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgnk_b200.so")
 
-GNK_MAX_BASIS = 104
+GNK_MAX_BASIS = 256
 
 
 class Layout(C.Structure):

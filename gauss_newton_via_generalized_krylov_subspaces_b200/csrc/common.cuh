@@ -45,7 +45,7 @@ struct gnk_ctx {
   int ls_method = 0;                  // gnk_tsqr_ls_method: 0 automatic, 1 Householder TSQR only
 };
 
-constexpr int GNK_PARTIALS = 1 << 18;  // doubles (2 MiB)
+constexpr int GNK_PARTIALS = 1 << 19;  // doubles (4 MiB)
 constexpr int GNK_TICKETS = 64;
 
 // regions inside gnk_ctx::d_partials (doubles); one per call site so that no two kernels share scratch
@@ -152,7 +152,7 @@ __device__ __forceinline__ unsigned int total_blocks() { return gridDim.x * grid
 //                         gather data 2 x nranks x P2P_GMAX doubles; halo data 2 parities x 2 sides x P2P_HMAX doubles.
 // ------------------------------------------------------------------------------------------------
 constexpr int P2P_MAXR = 16;
-constexpr int64_t P2P_GMAX = (int64_t)GNK_MAX_BASIS * GNK_MAX_BASIS;  // largest gather: one R triangle
+constexpr int64_t P2P_GMAX = (int64_t)GNK_TSQR_MAX * GNK_TSQR_MAX;    // largest gather: one R triangle
 constexpr int64_t P2P_HMAX = 2 * 16384;                              // largest halo message: 2 grid rows of 16384
 constexpr size_t P2P_FLAG_BYTES = 4096;
 constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;

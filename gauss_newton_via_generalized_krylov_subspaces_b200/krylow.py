@@ -71,8 +71,7 @@ class GeneralizedKrylowSubspace:
 
     def _grow(self):
         if self.cap >= MAX_COLUMNS:
-            raise _lib.GnkError(f"Krylov basis wider than {MAX_COLUMNS} columns is not supported by the TSQR panel; "
-                                "pass krylow_restart")
+            raise _lib.GnkError(f"Krylov basis wider than {MAX_COLUMNS} columns is not supported; pass krylow_restart")
         new_cap = min(MAX_COLUMNS, max(self.cap * 2, 2), self.n_glob)
         V = self.rt.zeros(new_cap * self.ld)
         V[:self.k * self.ld].copy_(self.V[:self.k * self.ld])

@@ -34,7 +34,10 @@ extern "C" {
 #endif
 
 #define GNK_B200_ABI_VERSION 1
-#define GNK_MAX_BASIS 104 /* k <= 103 basis columns (+1 rhs column in the TSQR panel) */
+#define GNK_MAX_BASIS 256 /* k <= 255 basis columns (+1 rhs column in the least-squares panel) */
+#define GNK_TSQR_MAX 104  /* widest panel of the tiled Householder TSQR; wider panels (the reference's max_iter=200 runs
+                             without restart, bratu_pde_test.py:307-316) take the single-CTA Householder QR, which
+                             needs the whole panel (n_rows * (k+1) <= 2^22 doubles) and a single rank */
 
 typedef struct gnk_ctx gnk_ctx;
 

@@ -107,7 +107,7 @@ def test_residual_is_zero_at_solution(g):
 # ------------------------------------------------------------------------------------------------
 # basis kernels
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,k", [(1, 1), (2, 1), (7, 3), (1000, 7), (1001, 16), (4097, 17), (100003, 33), (65536, 103)])
+@pytest.mark.parametrize("n,k", [(1, 1), (2, 1), (7, 3), (1000, 7), (1001, 16), (4097, 17), (100003, 33), (65536, 103), (20000, 255)])
 def test_basis_kernels(g, n, k):
     _lib, device = _lib_mods()
     from gauss_newton_via_generalized_krylov_subspaces_b200.partition import flat_layout_fields
@@ -203,6 +203,22 @@ def test_tsqr_least_squares(g, n, k):
     assert rel(x, xr) < 1e-13 * max(cond, 10.0)
 
 
+@pytest.mark.parametrize("n,k", [(576, 104), (576, 177), (1000, 255), (300, 200), (16000, 130)])
+def test_wide_panel_least_squares(g, n, k):
+    """more than 103 columns: the single-CTA Householder QR (csrc/tsqr.cu: dense_qr_ls_kernel)"""
+    rs = np.random.RandomState(n + k)
+    A = rs.normal(size=(n, k)) @ (np.eye(k) + 0.1 * rs.normal(size=(k, k)))
+    y = rs.normal(size=n)
+    x = g.linear_least_squares(A, y)
+    xr = np.linalg.lstsq(A, y, rcond=None)[0]
+    assert rel(x, xr) < 1e-13 * max(np.linalg.cond(A), 10.0)
+    v = _raw_ls(g, A, y, -1.0)
+    Ad = -A @ v[:k]
+    assert abs(v[k] - Ad @ Ad) <= 1e-10 * (Ad @ Ad) and abs(v[k + 1] - np.sum((y - Ad) ** 2)) <= 1e-10 * (y @ y)
+    assert v[k + 2] == 0 and abs(v[k + 3] - v[:k] @ v[:k]) <= 1e-12 * (v[:k] @ v[:k])
+    assert np.allclose(np.abs(v[k + 4:2 * k + 4]), np.abs(np.diag(np.linalg.qr(A, mode="r"))), rtol=1e-10)
+
+
 @pytest.mark.parametrize("n,k", [(16384, 1), (16385, 2), (20001, 7), (33333, 8), (50001, 12), (65537, 15), (70001, 16),
                                  (40003, 23), (100001, 24), (262147, 31)])
 def test_tsqr_warp_autonomous_leaf(g, n, k):
@@ -235,7 +251,7 @@ def _raw_ls(g, A, y, sign, householder=False, method=None):
         rt.upload(np.ascontiguousarray(A[:, j]), dA[j * lda:j * lda + n])
     dy = rt.zeros(lda)
     rt.upload(y, dy[:n])
-    out = rt.zeros(256)
+    out = rt.zeros(2 * 256 + 8)
     tsqr_solve(rt, dA, lda, n, k, dy, sign, out, householder=householder, method=method)
     return rt.read(out, 2 * k + 4).copy()
 
