@@ -19,7 +19,7 @@ from typing import Callable, Optional
 import numpy as np
 
 from . import _lib
-from .device import DeviceVector, NodeSharedBuffers, get_runtime, make_layout, ptr
+from .device import DeviceVector, NodeSharedBuffers, SharedBuffersUnavailable, get_runtime, make_layout, ptr
 from .partition import HALO, all_counts, stencil_layout_fields
 
 
@@ -180,8 +180,9 @@ class BratuDevice:
         return (hi - lo) * self.fields["m"]
 
     def d2h_doubles_per_vector(self):
-        """doubles that download_global moves device -> host on this rank: its own slab"""
-        return self.fields["n_own"]
+        """doubles that download_global moves device -> host on this rank: its own slab (the whole vector on the
+        fallback path without node-shared buffers)"""
+        return self.pb.n if self._shared is False else self.fields["n_own"]
 
     def resident(self, x_global):
         """upload a global host vector once; the returned DeviceVector can be passed to the solvers as x0"""
@@ -199,10 +200,16 @@ class BratuDevice:
         # that buffer.  (Round 1 all-gathered the full vector onto every GPU and copied it N times.)
         if self._shared is None:
             self._shared = NodeSharedBuffers(rt, self.pb.n)
-        host, finish = self._shared.acquire()
-        start = sum(self.counts[:rt.rank])
-        host[start:start + f["n_own"]].copy_(col[f["off"]:f["off"] + f["n_own"]], non_blocking=True)
-        return finish()
+        if self._shared is not False:
+            try:
+                host, finish = self._shared.acquire()
+            except SharedBuffersUnavailable:   # all ranks together (the failure is broadcast): /dev/shm is too small
+                self._shared = False
+            else:
+                start = sum(self.counts[:rt.rank])
+                host[start:start + f["n_own"]].copy_(col[f["off"]:f["off"] + f["n_own"]], non_blocking=True)
+                return finish()
+        return rt.download(self.allgather_device(col))   # fallback: all-gather on the devices, full copy per rank
 
     def allgather_device(self, col):
         """the global vector on EVERY rank's GPU (owned parts all-gathered over NVLink) -- for device-side consumers"""

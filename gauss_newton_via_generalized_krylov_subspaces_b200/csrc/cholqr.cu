@@ -1084,15 +1084,12 @@ int make_column_map(CUtensorMap* tm, const double* base, int m, int stored_rows,
   return 0;
 }
 
-constexpr int SG_CW = 8;  // consumer warps of the fused kernel
-
-template <int NB, int RU>
-int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu, const double* d_V,
+template <int NB, int RU, int CW>
+int run_stencil_gram_cw(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu, const double* d_V,
                      int64_t ldv, int v_cols, int k, const double* d_r, double sign, double* d_JV, int64_t ldjv,
                      double sign_a, double* d_out, cudaStream_t st) {
   if (int rc = ensure_scratch(ctx, st)) return rc;
   double* base = ctx->d_cholqr;
-  constexpr int CW = SG_CW;
   constexpr int PW = 8 * CW + 8, TJ = 8 * CW;
   const int stored_rows = lay->rows + 2 * lay->halo;
   CUtensorMap tmV, tmY, tmE;
@@ -1102,7 +1099,7 @@ int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, 
   if (int rc = make_column_map(&tmE, has_e ? d_expu : d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
   auto kern = stencil_gram_kernel<NB, CW>;
   constexpr int dyn = sg_dyn_bytes<NB, CW>();
-  static bool attr_set[64] = {false};
+  static bool attr_set[64] = {false};  // one per template instance
   if (!attr_set[ctx->device & 63]) {
     GNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     attr_set[ctx->device & 63] = true;
@@ -1132,6 +1129,19 @@ int gnk_cholqr_try(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows,
   if (c <= 24) return run_cholqr<3, 1>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
   if (c <= 32) return run_cholqr<4, 1>(ctx, d_A, lda, n_rows, k, d_y, sign_a, d_out, st);
   return 1;
+}
+
+// consumer warps of the fused kernel: 8 (64-point tiles) by default; GNK_SG_CW=10 selects 80-point tiles (development)
+template <int NB, int RU>
+int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu, const double* d_V,
+                     int64_t ldv, int v_cols, int k, const double* d_r, double sign, double* d_JV, int64_t ldjv,
+                     double sign_a, double* d_out, cudaStream_t st) {
+  static const int cw = getenv("GNK_SG_CW") ? atoi(getenv("GNK_SG_CW")) : 8;
+  if (cw == 10)
+    return run_stencil_gram_cw<NB, RU, 10>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a,
+                                           d_out, st);
+  return run_stencil_gram_cw<NB, RU, 8>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a, d_out,
+                                        st);
 }
 
 // gnk_stencil_gram_ls (gnk_b200.h): J V_k written AND the projected least squares solved with the panel read once.

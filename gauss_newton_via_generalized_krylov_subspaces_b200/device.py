@@ -200,6 +200,10 @@ class _Mark:
         return False
 
 
+class SharedBuffersUnavailable(RuntimeError):
+    """raised on EVERY rank together when /dev/shm cannot hold another result buffer"""
+
+
 class NodeSharedBuffers:
     """Host result buffers shared by the ranks of ONE node (files in /dev/shm mapped by every rank, page-locked with
     cudaHostRegister): a rank copies only ITS slab device -> host, and every rank still sees the whole vector -- the
@@ -226,10 +230,23 @@ class NodeSharedBuffers:
         if i >= 16:
             raise _lib.GnkError("more than 16 full-vector results are alive at once; copy or drop some")
         nbytes = 8 * self.n
+        ok = [True]
         if rt.rank == 0:
-            with open(self._path(i), "wb") as f:
-                f.truncate(nbytes)
-        rt.torch.distributed.barrier()
+            try:
+                fd0 = os.open(self._path(i), os.O_RDWR | os.O_CREAT | os.O_EXCL, 0o600)
+                try:
+                    os.posix_fallocate(fd0, 0, nbytes)  # reserve the pages now: a full /dev/shm must not end in SIGBUS
+                finally:
+                    os.close(fd0)
+            except OSError:
+                ok[0] = False
+                try:
+                    os.unlink(self._path(i))
+                except OSError:
+                    pass
+        rt.torch.distributed.broadcast_object_list(ok, src=0)
+        if not ok[0]:
+            raise SharedBuffersUnavailable(f"/dev/shm cannot hold a {nbytes >> 20} MiB result buffer")
         fd = os.open(self._path(i), os.O_RDWR)
         try:
             mm = mmap.mmap(fd, nbytes)

@@ -328,7 +328,8 @@ def gauss_newton_krylow(
             # panel in the same sweep (gnk_stencil_gram_ls); it answers 1 when the panel does not qualify
             if (is_bratu and ls_solver == "qr" and ls_method == 0 and not jac_ev.transposed
                     and jac_ev.scale == 1.0):
-                with rt.mark("spmm+ls", 8.0 * n_res_own * (2 * k + 2)) as mk:
+                # algorithmic bytes: the SpMM's 16nk + 8n plus the least-squares panel once, 8n(k+1)
+                with rt.mark("spmm+ls", 8.0 * n_res_own * (3 * k + 2)) as mk:
                     rc = lib.gnk_stencil_gram_ls(rt.ctx, C.byref(sol_lay), C.byref(prob.d.prm), ptr(jac_ev.expu),
                                                  ptr(krylow.V), ld, krylow.cap, k, ptr(F_cur), -1.0, ptr(JV), ldjv,
                                                  -1.0, ptr(blk), rt.stream)

@@ -43,26 +43,32 @@ def _envelope(golden_run, perturbed_run):
     return np.concatenate([env, np.full(len(a) - n, env[-1] if n else 0.0)])
 
 
-def sensitivity_bound(golden_run, perturbed_runs, ls_perturbed_run=None, floor=1e-10, factor=30.0, ls_factor=3.0):
-    """Per-iteration tolerance for the large grids, from the conditioning of the REFERENCE's own trajectory:
+def sensitivity_bound(golden_run, perturbed_runs, ls_perturbed_run=None, floor=1e-10, factor=3.0, window=1):
+    """Per-iteration tolerance for the large grids, from the conditioning of the REFERENCE's own trajectory.
 
-    * ``perturbed_runs``: the unmodified reference re-run with its start vector perturbed by one unit in the last place
-      (oracle/gen_golden.py:sensitivity; one run or several draws of the random sign pattern -- the largest envelope per
-      iteration counts).  An independent implementation is held to ``factor`` x the running maximum of that envelope;
-    * ``ls_perturbed_run`` (optional): the reference re-run with every projected least-squares solution it computes
-      moved by one ulp per component (oracle/gen_golden.py:sensitivity_ls).  On the fine grids the first iterates are
-      formed by a ~1e7-fold cancellation (x_1 = (c + d) v_0), so ONE ulp of d is ~1e-9 of x_1 -- an effect the u0
-      perturbation cannot show (the rounded d stays the same double) and no implementation with another summation
-      order can avoid.  Held to ``ls_factor`` x that envelope;
-    * never below ``floor`` = the 1e-10 bar of the north star, which is what applies wherever the reference's
-      trajectory is that well determined (from iteration ~10 on, and at the end)."""
+    Fixtures (oracle/gen_golden.py), all produced by the unmodified reference:
+    * ``perturbed_runs``: the reference re-run with its start vector u0 perturbed by one unit in the last place (random
+      signs; several draws).  On the fine grids the outcome is bimodal: usually the rounded least-squares solution d of
+      the first iterations stays the same double and the trace moves by ~1e-11; when it flips by one ulp (one draw of
+      three at 4096^2) the first iterates move by 2e-9 .. 4e-9, because x_1 = (c + d) v_0 is formed by a ~1e7-fold
+      cancellation;
+    * ``ls_perturbed_run``: the reference re-run with every projected least-squares solution moved by one ulp per
+      component (``sensitivity_ls``) -- the same mechanism, provoked deliberately: 1.1e-9 at iteration 1, 1.6e-9 at
+      iterations 3-4, decaying to 1e-10 by iteration 9 and 2e-11 by iteration 13.
+    No independent implementation (other summation order, FMA contraction, another exp) can reproduce the rounding of
+    d, so it is held to ``factor`` (3) x the LARGEST deviation the reference shows against itself at that iteration
+    (+- ``window`` iterations) over all fixtures -- and never below ``floor`` = the 1e-10 bar of the north star, which is
+    what applies wherever the reference's trajectory is that well determined (from iteration ~12 on, and at the end).
+    (Round 1 used 100 x the running maximum of a single u0 draw.)"""
     if isinstance(perturbed_runs, dict):
         perturbed_runs = [perturbed_runs]
-    env = np.maximum.reduce([_envelope(golden_run, p) for p in perturbed_runs])
-    bound = np.maximum(floor, factor * np.maximum.accumulate(env))
+    envs = [_envelope(golden_run, p) for p in perturbed_runs]
     if ls_perturbed_run is not None:
-        bound = np.maximum(bound, ls_factor * np.maximum.accumulate(_envelope(golden_run, ls_perturbed_run)))
-    return bound
+        envs.append(_envelope(golden_run, ls_perturbed_run))
+    env = np.maximum.reduce(envs)
+    n = len(env)
+    win = np.array([env[max(0, i - window):min(n, i + window + 1)].max() for i in range(n)])
+    return np.maximum(floor, factor * win)
 
 
 def bound_for(name, rname, floor=1e-10):

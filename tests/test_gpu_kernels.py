@@ -122,7 +122,7 @@ def test_basis_kernels(g, n, k):
     V = rt.zeros(k * ld)
     for j in range(k):
         rt.upload(Vh[j], V[j * ld:j * ld + n])
-    dc, ddv, dw, x = rt.zeros(128), rt.zeros(128), rt.zeros(ld), rt.zeros(ld)
+    dc, ddv, dw, x = rt.zeros(256), rt.zeros(256), rt.zeros(ld), rt.zeros(ld)
     rt.upload(c, dc[:k])
     rt.upload(dd, ddv[:k])
     rt.upload(w, dw[:n])
@@ -152,7 +152,7 @@ def test_basis_kernels(g, n, k):
                                  device.ptr(flag), rt.stream))
     assert rt.read_i32(flag)[0] == 1  # breakdown: max|w| <= 1e-8 (krylow.py:66)
     # Gram-Schmidt halves
-    h = rt.zeros(128)
+    h = rt.zeros(256)
     _lib.check(lib.gnk_cgs_dots(rt.ctx, C.byref(lay), device.ptr(V), k, device.ptr(dw), device.ptr(h), rt.stream))
     href = Vh @ w
     assert rel(rt.read(h, k), href) < 1e-12
@@ -649,9 +649,14 @@ def test_tsqr_degenerate_inputs(g, capsys):
     assert np.all(g.linear_least_squares(A, np.zeros(3000)) == 0.0)
     x = g.linear_least_squares(np.array([[2.0]]), np.array([3.0]))
     assert x.shape == (1,) and abs(x[0] - 1.5) < 1e-15
-    B = rs.normal(size=(104, 103))                       # square-ish, k = 103 = the panel limit
+    B = rs.normal(size=(104, 103))                       # square-ish, k = 103 = the limit of the tiled TSQR
     xb = g.linear_least_squares(B, rs.normal(size=104))
     assert np.all(np.isfinite(xb))
+    yb = rs.normal(size=200)
+    B = rs.normal(size=(200, 104))                       # one more column: the single-CTA wide-panel QR
+    assert rel(g.linear_least_squares(B, yb), np.linalg.lstsq(B, yb, rcond=None)[0]) < 1e-11
     from gauss_newton_via_generalized_krylov_subspaces_b200._lib import GnkError
-    with pytest.raises(GnkError):
-        g.linear_least_squares(rs.normal(size=(200, 104)), rs.normal(size=200))
+    with pytest.raises(GnkError):                        # beyond GNK_MAX_BASIS - 1 = 255 columns
+        g.linear_least_squares(rs.normal(size=(400, 256)), rs.normal(size=400))
+    with pytest.raises(GnkError):                        # wide AND tall: the single-CTA path is for small panels
+        g.linear_least_squares(rs.normal(size=(40000, 110)), rs.normal(size=40000))

@@ -113,7 +113,7 @@ def main():
             F_col = F
             report("spmm_ls", k, timeit(lambda: lib.gnk_stencil_gram_ls(
                 rt.ctx, lay, prm, ptr(E), ptr(V), ld, kmax, k, ptr(F_col), -1.0, ptr(JV), n, -1.0, ptr(blk),
-                rt.stream)), 8.0 * n * (2 * k + 2))
+                rt.stream)), 8.0 * n * (3 * k + 2))
     if a.out:
         os.makedirs(os.path.dirname(a.out), exist_ok=True)
         json.dump(dict(m=a.m, n=n, peak_gbs=peak, rows=rows), open(a.out, "w"), indent=1)
