@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(TPB) normalize_halo_kernel(const double* __res
   const bool bad = (mx <= atol);
   if (blockIdx.x == 0 && threadIdx.x == 0) *flag = bad ? 1 : 0;
   const int parity = (int)(hp.seq & 1ull);
+  bool remote = false;
   if (!bad) {
     const double nrm = sqrt(ss);
     double* lo_dst = hp.has_lo ? reinterpret_cast<double*>(static_cast<char*>(hp.peers[hp.rank - 1]) +
@@ -166,10 +167,18 @@ __global__ void __launch_bounds__(TPB) normalize_halo_kernel(const double* __res
       v.y = v.y / nrm;
       st2(out + 2 * i, v);
       const int64_t e = 2 * i;  // off, cnt and rows_m are even: a pair never straddles a piece
-      if (lo_dst && e >= hp.off && e < lo_end) st2(lo_dst + (e - hp.off), v);
-      if (hi_dst && e >= hi_beg && e < hi_end) st2(hi_dst + (e - hi_beg), v);
+      if (lo_dst && e >= hp.off && e < lo_end) {
+        st2(lo_dst + (e - hp.off), v);
+        remote = true;
+      }
+      if (hi_dst && e >= hi_beg && e < hi_end) {
+        st2(hi_dst + (e - hi_beg), v);
+        remote = true;
+      }
     }
-    __threadfence_system();  // this thread's remote stores are visible before the CTA takes its ticket
+    // this thread's remote stores are visible system-wide before the CTA takes its ticket (only the few border threads
+    // pay for the system-scope fence)
+    if (remote) __threadfence_system();
   }
   if (!grid_arrive_last(ticket)) return;
   char* mine = static_cast<char*>(hp.peers[hp.rank]);
@@ -184,13 +193,24 @@ __global__ void __launch_bounds__(TPB) normalize_halo_kernel(const double* __res
   }
   __syncthreads();
   if (bad) return;
-  if (hp.has_lo) {
-    const double* g = reinterpret_cast<const double*>(mine + p2p_halo_off(hp.nranks, parity, 0));
-    for (int64_t i = threadIdx.x; i < hp.cnt; i += blockDim.x) out[hp.off - hp.cnt + i] = ld_volatile(g + i);
-  }
-  if (hp.has_hi) {
-    const double* g = reinterpret_cast<const double*>(mine + p2p_halo_off(hp.nranks, parity, 1));
-    for (int64_t i = threadIdx.x; i < hp.cnt; i += blockDim.x) out[hp.off + hp.rows_m + i] = ld_volatile(g + i);
+  // The received rows were written by the peers BEFORE their flags (release) and are read after the acquire above;
+  // .cg loads (L2, never a stale L1 line), 128 bits wide and four in flight per thread: the 2 x 64 KB copy by one CTA
+  // took ~45 us with one 8-byte volatile load at a time (measured at 8 GPUs: normalize 51 us instead of 8)
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? hp.has_lo : hp.has_hi)) continue;
+    const double2* g = reinterpret_cast<const double2*>(mine + p2p_halo_off(hp.nranks, parity, side));
+    double2* dst = reinterpret_cast<double2*>(out + (side == 0 ? hp.off - hp.cnt : hp.off + hp.rows_m));
+    const int64_t nv2 = hp.cnt >> 1;
+    int64_t i = threadIdx.x;
+    for (; i + 3 * (int64_t)blockDim.x < nv2; i += 4 * (int64_t)blockDim.x) {
+      const double2 a = __ldcg(g + i), b = __ldcg(g + i + blockDim.x), c = __ldcg(g + i + 2 * blockDim.x),
+                    d = __ldcg(g + i + 3 * blockDim.x);
+      dst[i] = a;
+      dst[i + blockDim.x] = b;
+      dst[i + 2 * blockDim.x] = c;
+      dst[i + 3 * blockDim.x] = d;
+    }
+    for (; i < nv2; i += blockDim.x) dst[i] = __ldcg(g + i);
   }
 }
 

@@ -93,7 +93,8 @@ def main():
         rec = Recorder(gr["sample_idx"], err)
         out = g.gauss_newton_krylow(res, u0, jac, callback=rec, max_iter=31)
         check_trace(rec, gr, bound_for("bratu_g4097", "gnk_k30"))
-        assert (out.nit, out.nrev, out.njev) == (30, 31, 30) and gather_equal(out.x)
+        assert (out.nit, out.nrev, out.njev) == (int(gr["nit"]), int(gr["nfev"]), int(gr["njev"])), (out.nit, out.nrev, out.njev)
+        assert gather_equal(out.x)
         xs = np.array(rec.xs)
         d = np.max(np.abs(xs - gr["xs"]) / np.max(np.abs(gr["xs"]), axis=1, keepdims=True), axis=1)
         assert d[12:].max() < 1e-10, d[12:].max()                       # the plain bar from iteration 13 on
