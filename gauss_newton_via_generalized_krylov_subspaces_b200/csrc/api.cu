@@ -1,4 +1,6 @@
 // api.cu -- context lifecycle and error reporting of the gnk_b200 C ABI.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 void gnk_comm_teardown(gnk_ctx* ctx);
@@ -14,6 +16,11 @@ int gnk_fail(const char* what, cudaError_t e, const char* file, int line) {
   snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
   g_err = buf;
   return -1;
+}
+
+bool gnk_pdl_enabled() {
+  static const bool on = !(getenv("GNK_PDL") && atoi(getenv("GNK_PDL")) == 0);
+  return on;
 }
 
 extern "C" {

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(TPBX) residual_kernel(gnk_layout lay, gnk_brat
                                                          double* __restrict__ loss, gnk_p2p_dev pd) {
   __shared__ double sh[32];
   constexpr int W = VEC ? 2 : 1;
+  pdl_begin();
   const int m = lay.m;
   const int j0 = W * (blockIdx.x * TPBX + threadIdx.x);
   const int rbeg = -depth + (int)blockIdx.y * TR;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(TPBX) apply_kernel(gnk_layout lay, gnk_bratu p
                                                       int transpose, int TR, double* __restrict__ out,
                                                       int64_t out_ld, int64_t out_off) {
   constexpr int W = VEC ? 2 : 1;
+  pdl_begin();
   const int m = lay.m;
   const int col = blockIdx.x;
   const int j0 = W * (blockIdx.y * TPBX + threadIdx.x);
@@ -266,11 +268,11 @@ int gnk_bratu_residual(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm
   double* part = ctx->d_partials + PART_RESID;
   const gnk_p2p_dev pd = p2p_next(ctx);
   if (vec)
-    residual_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, d_u, d_y, d_F, d_expu, depth, tr, part,
-                                                                 ctx->d_tickets + TK_RESID, d_loss, pd);
+    GNK_CUDA(gnk_launch(residual_kernel<true>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, d_u, d_y, d_F, d_expu,
+                        depth, tr, part, ctx->d_tickets + TK_RESID, d_loss, pd));
   else
-    residual_kernel<false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, d_u, d_y, d_F, d_expu, depth, tr, part,
-                                                                  ctx->d_tickets + TK_RESID, d_loss, pd);
+    GNK_CUDA(gnk_launch(residual_kernel<false>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, d_u, d_y, d_F,
+                        d_expu, depth, tr, part, ctx->d_tickets + TK_RESID, d_loss, pd));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -289,11 +291,11 @@ int gnk_stencil_apply(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm,
   GNK_REQUIRE(grid.z <= 65535, "gnk_stencil_apply: too many row tiles");
   const double* e = (prm->lam == 0.0) ? nullptr : d_expu;
   if (vec)
-    apply_kernel<true><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr, d_out,
-                                                              out_ld, out_off);
+    GNK_CUDA(gnk_launch(apply_kernel<true>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, e, d_in, in_ld, sign,
+                        transpose, tr, d_out, out_ld, out_off));
   else
-    apply_kernel<false><<<grid, TPBX, 0, (cudaStream_t)stream>>>(*lay, *prm, e, d_in, in_ld, sign, transpose, tr, d_out,
-                                                               out_ld, out_off);
+    GNK_CUDA(gnk_launch(apply_kernel<false>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, e, d_in, in_ld, sign,
+                        transpose, tr, d_out, out_ld, out_off));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }

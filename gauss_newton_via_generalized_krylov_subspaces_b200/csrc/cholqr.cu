@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(GT, 1)
   __shared__ __align__(16) double red[NBLK * 64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  pdl_begin();
   const double* cp[NB];
 #pragma unroll
   for (int I = 0; I < NB; ++I) cp[I] = column_ptr(src, 8 * I + g);
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(RT, 1)
                          double* __restrict__ gout) {
   __shared__ double ds[KC];
   __shared__ double wsum[RT / 32][KC + 1];
+  pdl_begin();
   if (*status != 0) return;  // the CholeskyQR2 form was chosen, or pass 1 refused (uniform across the grid)
   const int k = src.k;
   for (int j = threadIdx.x; j < KC; j += RT) ds[j] = (j < k) ? sign * d0g[j] : 0.0;
@@ -476,6 +478,7 @@ __global__ void __launch_bounds__(FT) cholqr_factor1_kernel(const double* __rest
   __shared__ double gsh[NE_MAX];
   const int c = k + 1;
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  pdl_begin();
   if (pd.peers) {
     // compute step + collective in one kernel: this single CTA runs the mailbox all-reduce of the rank's Gram matrix
     // itself (p2p_tail_allreduce, common.cuh: stores into the peers' HBM over NVLink, flags, rank-ordered sum)
@@ -528,6 +531,7 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
   __shared__ double diag[MAXC];
   const int c = k + 1;
   const int i = threadIdx.x >> 5, l = threadIdx.x & 31;
+  pdl_begin();
   if (pd.peers) {
     // the mailbox all-reduce of [g, sum rho^2 | G2] comes first and unconditionally: every collective of the channel
     // must be executed by every rank (the double-buffered slots rely on it), whatever the status word says
@@ -686,8 +690,8 @@ int launch_refine(gnk_ctx* ctx, const PanelSource& src, double sign, double* bas
   if (ctas * GRAN > src.n_rows) ctas = ceil_div(src.n_rows, GRAN);
   const int64_t rows_per_cta = ceil_div(ceil_div(src.n_rows, ctas), GRAN) * GRAN;
   ctas = ceil_div(src.n_rows, rows_per_cta);
-  kern<<<(unsigned)ctas, RT, 0, st>>>(src, sign, base + CQ_D0, status, rows_per_cta, base + CQ_PART,
-                                      ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL2);
+  GNK_CUDA(gnk_launch(kern, dim3((unsigned)ctas), dim3(RT), 0, st, src, sign, base + CQ_D0, status, rows_per_cta,
+                      base + CQ_PART, ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL2));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -723,9 +727,9 @@ int cholqr_tail(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, in
   const bool gather1 = multi && !pd1.peers;
   if (gather1)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
-  cholqr_factor1_kernel<<<1, FT, 0, st>>>(gather1 ? base + CQ_ALL : base + CQ_LOCAL, gather1 ? ctx->nranks : 1, NB, k,
-                                          sign, method, base + CQ_T, base + CQ_R1, base + CQ_D0, base + CQ_AUX, status,
-                                          pd1);
+  GNK_CUDA(gnk_launch(cholqr_factor1_kernel, dim3(1), dim3(FT), 0, st, gather1 ? base + CQ_ALL : base + CQ_LOCAL,
+                      gather1 ? ctx->nranks : 1, NB, k, sign, method, base + CQ_T, base + CQ_R1, base + CQ_D0,
+                      base + CQ_AUX, status, pd1));
   GNK_LAUNCH_CHECK(ctx);
   // pass 2: the refinement form by default (it returns at once unless the status word says 0); the second CholeskyQR2
   // pass only when the caller asked for it (gnk_tsqr_ls_method 2)
@@ -746,9 +750,9 @@ int cholqr_tail(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, in
   const bool gather2 = multi && !pd2.peers;
   if (gather2)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL2, base + CQ_ALL2, GPAD + NE, st)) return rc;
-  cholqr_factor2_kernel<<<1, FT, 0, st>>>(gather2 ? base + CQ_ALL2 : base + CQ_LOCAL2, gather2 ? ctx->nranks : 1, NB, k,
-                                          base + CQ_R1, base + CQ_T, base + CQ_D0, base + CQ_AUX, status,
-                                          method == 2 ? 1 : 0, d_out, pd2);
+  GNK_CUDA(gnk_launch(cholqr_factor2_kernel, dim3(1), dim3(FT), 0, st, gather2 ? base + CQ_ALL2 : base + CQ_LOCAL2,
+                      gather2 ? ctx->nranks : 1, NB, k, base + CQ_R1, base + CQ_T, base + CQ_D0, base + CQ_AUX, status,
+                      method == 2 ? 1 : 0, d_out, pd2));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -765,8 +769,8 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
   const int64_t rows_per_cta = ceil_div(ceil_div(n_rows, ctas), GRAN) * GRAN;
   ctas = ceil_div(n_rows, rows_per_cta);
   // pass 1 and its factorisation
-  cholqr_gram_kernel<NB, RU><<<(unsigned)ctas, GT, 0, st>>>(src, rows_per_cta, base + CQ_PART,
-                                                        ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL);
+  GNK_CUDA(gnk_launch(cholqr_gram_kernel<NB, RU>, dim3((unsigned)ctas), dim3(GT), 0, st, src, rows_per_cta,
+                      base + CQ_PART, ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL));
   GNK_LAUNCH_CHECK(ctx);
   return cholqr_tail<NB, RU>(ctx, d_A, lda, n_rows, k, d_y, sign, d_out, st);
 }
@@ -879,6 +883,7 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_begin();  // the ring is set up while the predecessor drains; nothing global has been touched yet
 
   double acc[NBLK][2];
 #pragma unroll
@@ -1110,8 +1115,8 @@ int run_stencil_gram_cw(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* pr
   const int64_t ntask = (int64_t)ntj * ceil_div(lay->rows, TI);
   const int ctas = (int)(ntask < ctx->sm_count ? ntask : ctx->sm_count);
   StencilPanel p{lay->m, lay->rows, k, has_e ? 1 : 0, ldjv, prm->c_lap, prm->c_adv, prm->lam, sign};
-  kern<<<ctas, 32 * (CW + 1), dyn, st>>>(tmV, tmY, tmE, p, TI, d_JV, base + CQ_PART, ctx->d_tickets + TK_CHOLQR,
-                                        base + CQ_LOCAL);
+  GNK_CUDA(gnk_launch(kern, dim3(ctas), dim3(32 * (CW + 1)), (size_t)dyn, st, tmV, tmY, tmE, p, TI, d_JV, base + CQ_PART,
+                      ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL));
   GNK_LAUNCH_CHECK(ctx);
   return cholqr_tail<NB, RU>(ctx, d_JV, ldjv, lay->n_own, k, d_r + lay->off, sign_a, d_out, st);
 }

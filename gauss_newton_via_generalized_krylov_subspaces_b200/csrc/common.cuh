@@ -252,3 +252,33 @@ __device__ __forceinline__ double apply_refbits(double cu, double cl, double dg,
 }
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch between the ~11 kernels of an outer iteration.  A kernel launched with gnk_launch may
+// be scheduled as soon as every CTA of its predecessor has passed pdl_begin(): its CTAs become resident while the
+// predecessor drains and start the instant it has completed, which hides the launch latency and the block-scheduling
+// ramp between dependent kernels (2-3 us each; ~30 us per outer iteration in the latency regime: the 8-GPU slabs, the
+// 1024^2 grid).  pdl_begin() is the first statement of every such kernel: it waits until the predecessor has completed
+// and its memory operations are visible (so neither read-after-write nor write-after-read hazards can arise: nothing
+// global is touched before it), then lets the successor be scheduled.  Launched without the attribute, both
+// instructions are no-ops.  GNK_PDL=0 switches the attribute off.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_begin() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool gnk_pdl_enabled();
+template <typename... P, typename... A>
+inline cudaError_t gnk_launch(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = gnk_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(TPB) combine_kernel(const double* __restrict__
                                                        double* __restrict__ x, double* __restrict__ c_out,
                                                        double* __restrict__ cprev2) {
   __shared__ double coef[GNK_MAX_BASIS];
+  pdl_begin();
   for (int j = threadIdx.x; j < k; j += blockDim.x) coef[j] = d ? (c[j] + s * d[j]) : c[j];
   __syncthreads();
   if (blockIdx.x == 0) {
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(TPB) stats_kernel(const double* __restrict__ x
 __global__ void __launch_bounds__(TPB) normalize_kernel(const double* __restrict__ x, int64_t len,
                                                          const double* __restrict__ stats, double atol,
                                                          double* __restrict__ out, int32_t* flag) {
+  pdl_begin();
   const double ss = stats[0], mx = stats[1];
   const bool bad = (mx <= atol);
   if (blockIdx.x == 0 && threadIdx.x == 0) *flag = bad ? 1 : 0;
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(TPB) normalize_halo_kernel(const double* __res
                                                               const double* __restrict__ stats, double atol,
                                                               double* __restrict__ out, int32_t* flag, HaloPush hp,
                                                               unsigned int* ticket) {
+  pdl_begin();
   const double ss = stats[0], mx = stats[1];
   const bool bad = (mx <= atol);
   if (blockIdx.x == 0 && threadIdx.x == 0) *flag = bad ? 1 : 0;
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(TPB, 4) dots_kernel(const double* __restrict__
   // of traffic)
   __shared__ double wpart[TPB / 32][GNK_MAX_BASIS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  pdl_begin();
   for (int jb = 0; jb < k; jb += JB) {
     double acc[JB];
 #pragma unroll
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(TPB) update_kernel(const double* __restrict__ 
                                                       double* __restrict__ stats, gnk_p2p_dev pd) {
   __shared__ double coef[GNK_MAX_BASIS];
   __shared__ double sh[32];
+  pdl_begin();
   for (int j = threadIdx.x; j < k; j += blockDim.x) coef[j] = h[j];
   __syncthreads();
   const int64_t nv = n >> 1;
@@ -417,7 +422,8 @@ int gnk_combine_step(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int
   GNK_REQUIRE((lay->ld & 1) == 0, "gnk_combine: ld must be even");
   GNK_REQUIRE(d_c_out != d_c, "gnk_combine_step: c_out must not alias c (rejected trials re-read c)");
   int grid = stream_grid(ctx, lay->ld / 2, 8);
-  combine_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V, lay->ld, lay->ld, k, d_c, d_d, s, d_x, d_c_out, d_cprev2);
+  GNK_CUDA(gnk_launch(combine_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V, lay->ld, lay->ld, k, d_c, d_d, s,
+                      d_x, d_c_out, d_cprev2));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -442,7 +448,8 @@ int gnk_normalize(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, const 
   GNK_REQUIRE(ctx && lay && d_x && d_stats && d_out && d_flag, "gnk_normalize: null argument");
   GNK_REQUIRE((lay->ld & 1) == 0, "gnk_normalize: ld must be even");
   int grid = stream_grid(ctx, lay->ld / 2, 8);
-  normalize_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_x, lay->ld, d_stats, atol, d_out, d_flag);
+  GNK_CUDA(gnk_launch(normalize_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_x, lay->ld, d_stats, atol, d_out,
+                      d_flag));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -465,8 +472,8 @@ int gnk_normalize_halo(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, c
   HaloPush hp{ctx->d_p2p_peer, ctx->rank, ctx->nranks, lay->has_lo, lay->has_hi, lay->off, lay->n_own, cnt,
               ++ctx->p2p_hseq};
   int grid = stream_grid(ctx, lay->ld / 2, 8);
-  normalize_halo_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_x, lay->ld, d_stats, atol, d_out, d_flag, hp,
-                                                                ctx->d_tickets + TK_NORMALIZE);
+  GNK_CUDA(gnk_launch(normalize_halo_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_x, lay->ld, d_stats, atol,
+                      d_out, d_flag, hp, ctx->d_tickets + TK_NORMALIZE));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -477,9 +484,8 @@ int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, 
   GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_dots: k out of range");
   GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_dots: off/ld must be even");
   int grid = stream_grid(ctx, lay->n_own / 8, 8);  // >= 4 double2 per thread before another CTA is added
-  dots_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V + lay->off, lay->ld, lay->n_own, k, d_w + lay->off,
-                                                      ctx->d_partials + PART_DOTS, ctx->d_tickets + TK_DOTS, d_h,
-                                                      p2p_next(ctx));
+  GNK_CUDA(gnk_launch(dots_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V + lay->off, lay->ld, lay->n_own, k,
+                      d_w + lay->off, ctx->d_partials + PART_DOTS, ctx->d_tickets + TK_DOTS, d_h, p2p_next(ctx)));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -490,10 +496,9 @@ int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k
   GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_update: k out of range");
   GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_update: off/ld must be even");
   int grid = stream_grid(ctx, lay->n_own / 2, 8);
-  update_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(d_V + lay->off, lay->ld, lay->n_own, k, d_h,
-                                                        d_w + lay->off, ctx->d_partials + PART_UPDATE,
-                                                        ctx->d_tickets + TK_UPDATE, d_stats,
-                                                        d_stats ? p2p_next(ctx) : gnk_p2p_dev{nullptr, 0, 1, 0ull});
+  GNK_CUDA(gnk_launch(update_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V + lay->off, lay->ld, lay->n_own, k,
+                      d_h, d_w + lay->off, ctx->d_partials + PART_UPDATE, ctx->d_tickets + TK_UPDATE, d_stats,
+                      d_stats ? p2p_next(ctx) : gnk_p2p_dev{nullptr, 0, 1, 0ull}));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
