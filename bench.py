@@ -414,8 +414,8 @@ class Harness:
                  max_dev_over_bound=float(np.max(dev / bound)), within_bound=bool(np.all(dev <= bound)),
                  dev_per_iteration=[float(f"{v:.3e}") for v in dev],
                  bound_per_iteration=[float(f"{v:.3e}") for v in bound],
-                 bound="per iteration max(1e-10, 3 x the largest deviation the reference shows against itself at that "
-                       "iteration (+-1) under one-ulp changes of u0 (3 draws) and of its own projected least-squares "
+                 bound="per iteration max(1e-10, 10 x the largest deviation the reference shows against itself at that "
+                       "iteration (+-1) under ONE-ulp changes of u0 (3 draws) and of its own projected least-squares "
                        "solutions) (tests/golden_util.py:sensitivity_bound; fixtures by oracle/gen_golden.py)",
                  final_loss=float(loss), golden_final_loss=gl,
                  final_loss_dev=None if gl is None else float(abs(loss - gl) / gl))

@@ -18,9 +18,9 @@ int gnk_fail(const char* what, cudaError_t e, const char* file, int line) {
   return -1;
 }
 
-bool gnk_pdl_enabled() {
-  static const bool on = !(getenv("GNK_PDL") && atoi(getenv("GNK_PDL")) == 0);
-  return on;
+int gnk_pdl_mode() {
+  static const int mode = getenv("GNK_PDL") ? atoi(getenv("GNK_PDL")) : 1;
+  return mode;
 }
 
 extern "C" {

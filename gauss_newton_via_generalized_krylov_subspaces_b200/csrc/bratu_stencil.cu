@@ -268,10 +268,10 @@ int gnk_bratu_residual(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm
   double* part = ctx->d_partials + PART_RESID;
   const gnk_p2p_dev pd = p2p_next(ctx);
   if (vec)
-    GNK_CUDA(gnk_launch(residual_kernel<true>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, d_u, d_y, d_F, d_expu,
+    GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), residual_kernel<true>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, d_u, d_y, d_F, d_expu,
                         depth, tr, part, ctx->d_tickets + TK_RESID, d_loss, pd));
   else
-    GNK_CUDA(gnk_launch(residual_kernel<false>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, d_u, d_y, d_F,
+    GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), residual_kernel<false>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, d_u, d_y, d_F,
                         d_expu, depth, tr, part, ctx->d_tickets + TK_RESID, d_loss, pd));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
@@ -291,10 +291,10 @@ int gnk_stencil_apply(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm,
   GNK_REQUIRE(grid.z <= 65535, "gnk_stencil_apply: too many row tiles");
   const double* e = (prm->lam == 0.0) ? nullptr : d_expu;
   if (vec)
-    GNK_CUDA(gnk_launch(apply_kernel<true>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, e, d_in, in_ld, sign,
+    GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), apply_kernel<true>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, e, d_in, in_ld, sign,
                         transpose, tr, d_out, out_ld, out_off));
   else
-    GNK_CUDA(gnk_launch(apply_kernel<false>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, e, d_in, in_ld, sign,
+    GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), apply_kernel<false>, grid, dim3(TPBX), 0, (cudaStream_t)stream, *lay, *prm, e, d_in, in_ld, sign,
                         transpose, tr, d_out, out_ld, out_off));
   GNK_LAUNCH_CHECK(ctx);
   return 0;

@@ -690,7 +690,7 @@ int launch_refine(gnk_ctx* ctx, const PanelSource& src, double sign, double* bas
   if (ctas * GRAN > src.n_rows) ctas = ceil_div(src.n_rows, GRAN);
   const int64_t rows_per_cta = ceil_div(ceil_div(src.n_rows, ctas), GRAN) * GRAN;
   ctas = ceil_div(src.n_rows, rows_per_cta);
-  GNK_CUDA(gnk_launch(kern, dim3((unsigned)ctas), dim3(RT), 0, st, src, sign, base + CQ_D0, status, rows_per_cta,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(src.n_rows), kern, dim3((unsigned)ctas), dim3(RT), 0, st, src, sign, base + CQ_D0, status, rows_per_cta,
                       base + CQ_PART, ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL2));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
@@ -727,7 +727,7 @@ int cholqr_tail(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, in
   const bool gather1 = multi && !pd1.peers;
   if (gather1)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL, base + CQ_ALL, NE, st)) return rc;
-  GNK_CUDA(gnk_launch(cholqr_factor1_kernel, dim3(1), dim3(FT), 0, st, gather1 ? base + CQ_ALL : base + CQ_LOCAL,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(n_rows), cholqr_factor1_kernel, dim3(1), dim3(FT), 0, st, gather1 ? base + CQ_ALL : base + CQ_LOCAL,
                       gather1 ? ctx->nranks : 1, NB, k, sign, method, base + CQ_T, base + CQ_R1, base + CQ_D0,
                       base + CQ_AUX, status, pd1));
   GNK_LAUNCH_CHECK(ctx);
@@ -750,7 +750,7 @@ int cholqr_tail(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, in
   const bool gather2 = multi && !pd2.peers;
   if (gather2)
     if (int rc = gnk_comm_allgather_doubles(ctx, base + CQ_LOCAL2, base + CQ_ALL2, GPAD + NE, st)) return rc;
-  GNK_CUDA(gnk_launch(cholqr_factor2_kernel, dim3(1), dim3(FT), 0, st, gather2 ? base + CQ_ALL2 : base + CQ_LOCAL2,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(n_rows), cholqr_factor2_kernel, dim3(1), dim3(FT), 0, st, gather2 ? base + CQ_ALL2 : base + CQ_LOCAL2,
                       gather2 ? ctx->nranks : 1, NB, k, base + CQ_R1, base + CQ_T, base + CQ_D0, base + CQ_AUX, status,
                       method == 2 ? 1 : 0, d_out, pd2));
   GNK_LAUNCH_CHECK(ctx);
@@ -769,7 +769,7 @@ int run_cholqr(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int
   const int64_t rows_per_cta = ceil_div(ceil_div(n_rows, ctas), GRAN) * GRAN;
   ctas = ceil_div(n_rows, rows_per_cta);
   // pass 1 and its factorisation
-  GNK_CUDA(gnk_launch(cholqr_gram_kernel<NB, RU>, dim3((unsigned)ctas), dim3(GT), 0, st, src, rows_per_cta,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(n_rows), cholqr_gram_kernel<NB, RU>, dim3((unsigned)ctas), dim3(GT), 0, st, src, rows_per_cta,
                       base + CQ_PART, ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL));
   GNK_LAUNCH_CHECK(ctx);
   return cholqr_tail<NB, RU>(ctx, d_A, lda, n_rows, k, d_y, sign, d_out, st);
@@ -1115,7 +1115,7 @@ int run_stencil_gram_cw(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* pr
   const int64_t ntask = (int64_t)ntj * ceil_div(lay->rows, TI);
   const int ctas = (int)(ntask < ctx->sm_count ? ntask : ctx->sm_count);
   StencilPanel p{lay->m, lay->rows, k, has_e ? 1 : 0, ldjv, prm->c_lap, prm->c_adv, prm->lam, sign};
-  GNK_CUDA(gnk_launch(kern, dim3(ctas), dim3(32 * (CW + 1)), (size_t)dyn, st, tmV, tmY, tmE, p, TI, d_JV, base + CQ_PART,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), kern, dim3(ctas), dim3(32 * (CW + 1)), (size_t)dyn, st, tmV, tmY, tmE, p, TI, d_JV, base + CQ_PART,
                       ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL));
   GNK_LAUNCH_CHECK(ctx);
   return cholqr_tail<NB, RU>(ctx, d_JV, ldjv, lay->n_own, k, d_r + lay->off, sign_a, d_out, st);

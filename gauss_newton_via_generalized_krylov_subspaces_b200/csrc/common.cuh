@@ -261,15 +261,23 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // 1024^2 grid).  pdl_begin() is the first statement of every such kernel: it waits until the predecessor has completed
 // and its memory operations are visible (so neither read-after-write nor write-after-read hazards can arise: nothing
 // global is touched before it), then lets the successor be scheduled.  Launched without the attribute, both
-// instructions are no-ops.  GNK_PDL=0 switches the attribute off.
+// instructions are no-ops.  The attribute is set only for slabs of at most GNK_PDL_MAX_N unknowns (measured on one GPU:
+// 1024^2 restart 30 4236 -> 4498 it/s with it, 4096^2 371 -> 365 it/s: on big slabs the early-resident CTAs of the
+// successor take warp slots from a predecessor that is still streaming).  GNK_PDL=0 switches it off, GNK_PDL=2 forces it.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_begin() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-bool gnk_pdl_enabled();
+int gnk_pdl_mode();  // 0 off, 1 by size, 2 always
+constexpr int64_t GNK_PDL_MAX_N = 6 * 1024 * 1024;
+inline bool gnk_pdl_for(int64_t n_unknowns) {
+  const int mode = gnk_pdl_mode();
+  return mode == 2 || (mode == 1 && n_unknowns <= GNK_PDL_MAX_N);
+}
 template <typename... P, typename... A>
-inline cudaError_t gnk_launch(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+inline cudaError_t gnk_launch(bool pdl, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              A&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -277,7 +285,7 @@ inline cudaError_t gnk_launch(void (*kern)(P...), dim3 grid, dim3 block, size_t 
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = gnk_pdl_enabled() ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);

@@ -422,7 +422,7 @@ int gnk_combine_step(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int
   GNK_REQUIRE((lay->ld & 1) == 0, "gnk_combine: ld must be even");
   GNK_REQUIRE(d_c_out != d_c, "gnk_combine_step: c_out must not alias c (rejected trials re-read c)");
   int grid = stream_grid(ctx, lay->ld / 2, 8);
-  GNK_CUDA(gnk_launch(combine_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V, lay->ld, lay->ld, k, d_c, d_d, s,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), combine_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V, lay->ld, lay->ld, k, d_c, d_d, s,
                       d_x, d_c_out, d_cprev2));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
@@ -448,7 +448,7 @@ int gnk_normalize(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, const 
   GNK_REQUIRE(ctx && lay && d_x && d_stats && d_out && d_flag, "gnk_normalize: null argument");
   GNK_REQUIRE((lay->ld & 1) == 0, "gnk_normalize: ld must be even");
   int grid = stream_grid(ctx, lay->ld / 2, 8);
-  GNK_CUDA(gnk_launch(normalize_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_x, lay->ld, d_stats, atol, d_out,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), normalize_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_x, lay->ld, d_stats, atol, d_out,
                       d_flag));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
@@ -472,7 +472,7 @@ int gnk_normalize_halo(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, c
   HaloPush hp{ctx->d_p2p_peer, ctx->rank, ctx->nranks, lay->has_lo, lay->has_hi, lay->off, lay->n_own, cnt,
               ++ctx->p2p_hseq};
   int grid = stream_grid(ctx, lay->ld / 2, 8);
-  GNK_CUDA(gnk_launch(normalize_halo_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_x, lay->ld, d_stats, atol,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), normalize_halo_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_x, lay->ld, d_stats, atol,
                       d_out, d_flag, hp, ctx->d_tickets + TK_NORMALIZE));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
@@ -483,8 +483,10 @@ int gnk_cgs_dots(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k, 
   GNK_REQUIRE(ctx && lay && d_V && d_w && d_h, "gnk_cgs_dots: null argument");
   GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_dots: k out of range");
   GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_dots: off/ld must be even");
-  int grid = stream_grid(ctx, lay->n_own / 8, 8);  // >= 4 double2 per thread before another CTA is added
-  GNK_CUDA(gnk_launch(dots_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V + lay->off, lay->ld, lay->n_own, k,
+  // >= 4 double2 per thread before another CTA is added; 4 CTAs per SM are resident (launch bounds), more only lengthen
+  // the last CTA's reduction over the per-CTA partials
+  int grid = stream_grid(ctx, lay->n_own / 8, 4);
+  GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), dots_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V + lay->off, lay->ld, lay->n_own, k,
                       d_w + lay->off, ctx->d_partials + PART_DOTS, ctx->d_tickets + TK_DOTS, d_h, p2p_next(ctx)));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
@@ -496,7 +498,7 @@ int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k
   GNK_REQUIRE(k >= 1 && k <= GNK_MAX_BASIS, "gnk_cgs_update: k out of range");
   GNK_REQUIRE((lay->off & 1) == 0 && (lay->ld & 1) == 0, "gnk_cgs_update: off/ld must be even");
   int grid = stream_grid(ctx, lay->n_own / 2, 8);
-  GNK_CUDA(gnk_launch(update_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V + lay->off, lay->ld, lay->n_own, k,
+  GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), update_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_V + lay->off, lay->ld, lay->n_own, k,
                       d_h, d_w + lay->off, ctx->d_partials + PART_UPDATE, ctx->d_tickets + TK_UPDATE, d_stats,
                       d_stats ? p2p_next(ctx) : gnk_p2p_dev{nullptr, 0, 1, 0ull}));
   GNK_LAUNCH_CHECK(ctx);

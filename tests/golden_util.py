@@ -43,7 +43,7 @@ def _envelope(golden_run, perturbed_run):
     return np.concatenate([env, np.full(len(a) - n, env[-1] if n else 0.0)])
 
 
-def sensitivity_bound(golden_run, perturbed_runs, ls_perturbed_run=None, floor=1e-10, factor=3.0, window=1):
+def sensitivity_bound(golden_run, perturbed_runs, ls_perturbed_run=None, floor=1e-10, factor=10.0, window=1):
     """Per-iteration tolerance for the large grids, from the conditioning of the REFERENCE's own trajectory.
 
     Fixtures (oracle/gen_golden.py), all produced by the unmodified reference:
@@ -56,10 +56,13 @@ def sensitivity_bound(golden_run, perturbed_runs, ls_perturbed_run=None, floor=1
       component (``sensitivity_ls``) -- the same mechanism, provoked deliberately: 1.1e-9 at iteration 1, 1.6e-9 at
       iterations 3-4, decaying to 1e-10 by iteration 9 and 2e-11 by iteration 13.
     No independent implementation (other summation order, FMA contraction, another exp) can reproduce the rounding of
-    d, so it is held to ``factor`` (3) x the LARGEST deviation the reference shows against itself at that iteration
-    (+- ``window`` iterations) over all fixtures -- and never below ``floor`` = the 1e-10 bar of the north star, which is
-    what applies wherever the reference's trajectory is that well determined (from iteration ~12 on, and at the end).
-    (Round 1 used 100 x the running maximum of a single u0 draw.)"""
+    d: two backward-stable solvers of the same one-column problem differ by a handful of ulps (measured against
+    LAPACK's result: 0 ulp at 4096^2 on one GPU, 1 ulp on 2 and 8 GPUs, 6 ulp at 1024^2).  So the deviation is held to
+    ``factor`` (10, i.e. ten ulps of d) x the LARGEST deviation the reference shows against itself under a ONE-ulp
+    change, at that iteration (+- ``window`` iterations), over all fixtures -- and never below ``floor`` = the 1e-10 bar
+    of the north star, which is what applies wherever the reference's trajectory is that well determined (from
+    iteration ~16 on at 4096^2, ~3 on at 1024^2, and at the end).  (Round 1 used 100 x the RUNNING maximum of a
+    single u0 draw, which never came back down to 1e-10.)"""
     if isinstance(perturbed_runs, dict):
         perturbed_runs = [perturbed_runs]
     envs = [_envelope(golden_run, p) for p in perturbed_runs]
