@@ -160,18 +160,38 @@ def cpu_solve(problem, restart, iters, budget_s=None):
         return done[0], done[1], False
 
 
-def time_to_tolerance_cpu():
-    """the reference's converging configuration (bratu_pde_test.py:76-103): grid_nodes=101, grid_resolution=1"""
-    problem = cpu_problem(101, grid_resolution=1)
-    kind, solve, res, u0, jac, err = problem
-    t0 = time.perf_counter()
-    with contextlib.redirect_stdout(sys.stderr):
-        out = None
+# time-to-tolerance workloads: the reference's converging configuration compare_without_scaling (bratu_pde_test.py:76-103:
+# grid_nodes=101, grid_resolution=1, default version: 82 iterations) and the same set-up on larger grids with
+# version="res_new", which converges within max_iter=100 there (65 / 66 iterations; goldens by oracle/gen_golden.py ttt)
+TTT = (("bratu_g101_grid_resolution1_res_old", 101, "res_old"),
+       ("bratu_g513_grid_resolution1_res_new", 513, "res_new"),
+       ("bratu_g1025_grid_resolution1_res_new", 1025, "res_new"))
+
+
+def time_to_tolerance_cpu(max_grid=513):
+    out = []
+    from oracle import ref_loader
+    ref = ref_loader.load_reference()
+    for name, G, version in TTT:
+        if G > max_grid:
+            continue
+        kind, solve, res, u0, jac, err = cpu_problem(G, grid_resolution=1)
         xs = []
-        nit, success = solve(res, u0, jac, None, 100, lambda x=None, nfev=None, cg_iter=None: xs.append(x))
-    dt = time.perf_counter() - t0
-    return [dict(workload="bratu_g101_grid_resolution1_res_old", tol=1e-8, nit=int(nit), success=bool(success),
-                 seconds=dt, error=float(err(xs[-1])), kind=kind)]
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(sys.stderr):
+            if ref is not None:
+                o = ref.gauss_newton_krylow.gauss_newton_krylow(res, u0, jac, max_iter=100, version=version,
+                                                                callback=lambda x, nfev, cg_iter: xs.append(x))
+                nit, success = o.nit, o.success
+            else:
+                from oracle import gnk_oracle as orc
+                o = orc.gnk(res, u0, jac, max_iter=100, version=version,
+                            callback=lambda x=None, nfev=None, cg_iter=None: xs.append(x))
+                nit, success = o["nit"], o["success"]
+        dt = time.perf_counter() - t0
+        out.append(dict(workload=name, tol=1e-8, nit=int(nit), success=bool(success), seconds=dt,
+                        error=float(err(xs[-1])), kind=kind, impl="reference", cores=os.cpu_count()))
+    return out
 
 
 def run_reference(a):
@@ -439,8 +459,10 @@ class Harness:
                     dram.setdefault(k_, dict(v_, source=fn) if isinstance(v_, dict) else v_)
             except Exception:
                 pass
-        ncu_name = dict(ls="stencil_gram_ls", tsqr="cholqr", spmm="apply_kernel", combine="combine_kernel",
-                        cgs_dots="dots_kernel", cgs_update="update_kernel", residual="residual_kernel")
+        ncu_name = {"spmm+ls": "stencil_gram_ls"}
+        ncu_name.update(tsqr="cholqr", spmm="apply_kernel", combine="combine_kernel",
+                        cgs_dots="dots_kernel", cgs_update="update_kernel", residual="residual_kernel",
+                        spmv_t="apply_kernel", normalize="normalize_kernel")
         for name in kernels:
             ent = dram.get(ncu_name.get(name, ""), {})
             ratio = ent.get("ratio") if isinstance(ent, dict) else None
@@ -462,21 +484,25 @@ class Harness:
 
     # --------------------------------------------------------------------------------------------
     def time_to_tolerance(self):
-        """the reference's converging configuration (bratu_pde_test.py:76-103), host buffers in and out"""
+        """wall seconds until the solver's own stop test fires (tol = 1e-8), host buffers in and out"""
         g = self.g
-        pb = g.BratuPdeProblem(101, 5, 10, grid_resolution=1)
-        y = pb.pde_operator(pb.u_true)
-        u0 = pb.u_true + 0.1 * np.random.RandomState(42).normal(loc=0, scale=1, size=pb.n)
-        err = pb.make_error()
-        best, out = None, None
-        for _ in range(4):
-            self.torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            out = g.gauss_newton_krylow(pb.make_res(y), u0, pb.make_jac(), callback=lambda **k: None)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        return [dict(workload="bratu_g101_grid_resolution1_res_old", tol=1e-8, nit=int(out.nit), success=bool(out.success),
-                     seconds=best, error=float(err(out.x)), note="best of 4 (the first includes one-time allocations)")]
+        out = []
+        for name, G, version in TTT:
+            pb = g.BratuPdeProblem(G, 5, 10, grid_resolution=1)
+            y = pb.pde_operator(pb.u_true)
+            u0 = pb.u_true + 0.1 * np.random.RandomState(42).normal(loc=0, scale=1, size=pb.n)
+            err = pb.make_error()
+            best, o = None, None
+            for _ in range(4):
+                self.torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                o = g.gauss_newton_krylow(pb.make_res(y), u0, pb.make_jac(), callback=lambda **k: None, version=version,
+                                          max_iter=100)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            out.append(dict(workload=name, tol=1e-8, nit=int(o.nit), success=bool(o.success), seconds=best,
+                            error=float(err(o.x)), impl="ours", note="best of 4 (the first includes one-time allocations)"))
+        return out
 
 
 def run_ours(a):
@@ -522,7 +548,7 @@ def run_ours(a):
                           "iteration grows with k, so this flatters the CPU (the full matched solve is what "
                           "`bench.py --impl reference` times)")
         if ttt is not None:
-            ttt += [dict(t, impl="reference") for t in time_to_tolerance_cpu()]
+            ttt += time_to_tolerance_cpu()
 
     if rank == 0:
         cfg = workload_config(a, workload_spec(a), name, world)
