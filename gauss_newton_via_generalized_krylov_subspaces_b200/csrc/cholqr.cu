@@ -844,9 +844,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                "l"(tm), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void sts2(uint32_t a, double2 v) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
-}
 __device__ __forceinline__ double2 lds2(uint32_t a) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
@@ -1046,264 +1043,6 @@ __global__ void __launch_bounds__(32 * (CW + 1), 1)
   reduce_gram<NBLK, CW, NT>(acc, red, partials, ticket, Gout);
 }
 
-// ----------------------------------------------------------------------------------------------------------------------
-// Two warps per segment (NB >= 2).  ncu on the kernel above (8 consumer warps, 168 registers): FP64 pipe 57-61 % busy,
-// issue slots 33 %, top stall `wait` -- with two warps per SM sub-partition each warp's serial step (LDS -> 72 separately
-// rounded DMUL/DADD -> stores -> 20 DMMA) overlaps only partly with the other's, and more warps of that kind do not fit
-// the register file.  Here the two warps of a PAIR share one 8-point segment and split the column blocks: half 0 applies
-// the stencil to blocks [0, NBA), half 1 to [NBA, NB) (NBA = ceil(NB / 2)); both publish their tiles through a
-// double-buffered exchange buffer in shared memory, meet at a named barrier (bar.sync id = 1 + segment, 64 threads), read
-// the partner's tiles and accumulate HALF of the Gram blocks each (blocks in blk_index order: half 0 the first
-// ceil(NBLK / 2), half 1 the rest).  Per warp: half the window registers, half the accumulators, half the stencil and DMMA
-// work -- about 100 registers, so twice as many consumer warps are resident and each sub-partition always has a warp
-// whose DMMAs or DADDs are ready.  J V is bit-identical to the one-warp kernel; G differs by summation order only.
-// ----------------------------------------------------------------------------------------------------------------------
-template <int NB, int SW>
-__global__ void __launch_bounds__(32 * (2 * SW + 1), 1)
-    stencil_gram_pair_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmY,
-                             const __grid_constant__ CUtensorMap tmE, StencilPanel p, int TI, double* __restrict__ JV,
-                             double* __restrict__ partials, unsigned int* ticket, double* __restrict__ Gout) {
-  static_assert(NB >= 2, "the pair kernel splits column blocks");
-  constexpr int NBLK = nblocks(NB);
-  constexpr int NBA = (NB + 1) / 2;          // stencil blocks of half 0
-  constexpr int NBO = NBA;                   // register slots for own blocks (half 1 may use fewer)
-  constexpr int GH0 = (NBLK + 1) / 2;        // Gram blocks of half 0 (blk_index order)
-  constexpr int NACC = GH0;                  // accumulator slots per warp
-  constexpr int CW = SW;                     // tile width in segments (ring geometry as in the one-warp kernel)
-  constexpr int CWARPS = 2 * SW;
-  constexpr int SB = sg_slot_bytes<NB, CW>();
-  constexpr int XB = NB * 512;               // one exchange buffer: NB blocks x [8 columns][8 points]
-  constexpr int NS = ((200 * 1024 - 2 * SW * XB) / SB) < 16 ? ((200 * 1024 - 2 * SW * XB) / SB) : 16;
-  constexpr int TJ = 8 * CW, PB = sg_plane_bytes<CW>(), YE = sg_ye_bytes<CW>();
-  constexpr int NT = 32 * (CWARPS + 1);
-  extern __shared__ __align__(128) unsigned char ring[];
-  __shared__ __align__(16) double red[NBLK * 64];
-  __shared__ __align__(8) unsigned long long bars[2 * NS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int m = p.m;
-  const int ntj = (m + TJ - 1) / TJ;
-  const int nstrip = (p.rows + TI - 1) / TI;
-  const int64_t ntask = (int64_t)ntj * nstrip;
-  const uint32_t ring0 = smem_u32(ring), full0 = smem_u32(bars), empty0 = full0 + 8 * NS;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, CWARPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  pdl_begin();
-
-  double acc[NACC][2];
-#pragma unroll
-  for (int b = 0; b < NACC; ++b) acc[b][0] = acc[b][1] = 0.0;
-  const int seg = warp >> 1, half = warp & 1;
-
-  if (warp == CWARPS) {
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      const uint32_t tx = (uint32_t)((8 * NB + 1 + (p.has_e ? 1 : 0)) * PB);
-      for (int64_t task = blockIdx.x; task < ntask; task += gridDim.x) {
-        const int strip = (int)(task / ntj), tj = (int)(task - (int64_t)strip * ntj);
-        const int i0 = strip * TI, i1 = min(i0 + TI, p.rows), j0 = tj * TJ;
-        for (int r = i0 - 1; r <= i1; ++r) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1u);
-          const uint32_t dst = ring0 + s * SB, fb = full0 + 8 * s;
-          mbar_expect_tx(fb, tx);
-          tma_load_3d(dst, &tmV, j0 - 4, r + 2, 0, fb);
-          tma_load_2d(dst + 8 * NB * PB, &tmY, j0 - 4, r + 2, fb);
-          if (p.has_e) tma_load_2d(dst + 8 * NB * PB + YE, &tmE, j0 - 4, r + 2, fb);
-          if (++s == NS) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
-      }
-    }
-  } else {
-    const double sg = p.sign;
-    const double d0 = __dadd_rn(4.0 * p.c_lap, -p.c_adv);
-    const double cd = sg * __dadd_rn(-p.c_lap, p.c_adv), cu = sg * -p.c_lap, cl = sg * -p.c_lap;
-    const int blk0 = half ? NBA : 0;               // first own block
-    const int nown = half ? NB - NBA : NBA;        // own blocks
-    uint32_t poff[NBO];
-#pragma unroll
-    for (int q = 0; q < NBO; ++q) poff[q] = (uint32_t)((8 * (blk0 + (q < nown ? q : 0)) + g) * PB + 8 * (4 + 8 * seg + 2 * t));
-    // the last block (always half 1's last own block) may hold the residual column and padding
-    const int lastcol = 8 * (NB - 1) + g;
-    const int lastkind = lastcol < p.k ? 0 : (lastcol == p.k ? 1 : 2);
-    if (half == 1) {
-      if (lastkind == 1) poff[nown - 1] = (uint32_t)(8 * NB * PB + 8 * (4 + 8 * seg + 2 * t));
-      if (lastkind == 2) poff[nown - 1] = (uint32_t)(g * PB + 8 * (4 + 8 * seg + 2 * t));  // finite data, weight 0
-    }
-    const double wsel = (half == 1 && lastkind != 0) ? 0.0 : 1.0, wone = (half == 1 && lastkind == 1) ? 1.0 : 0.0;
-    const double cuL = wsel * cu, clL = wsel * cl, cdL = wsel * cd;
-    const uint32_t eoff = (uint32_t)(8 * NB * PB + YE + 8 * (4 + 8 * seg + 2 * t));
-    // exchange buffers of this pair, and this lane's place inside a block: column g, points 2t, 2t + 1
-    const uint32_t xb0 = ring0 + NS * SB + (uint32_t)(2 * seg) * XB;
-    const uint32_t xlane = (uint32_t)(g * 64 + t * 16);
-    uint32_t xsel = 0;
-    const int barid = 1 + seg;
-    uint32_t slot = 0, phase = 0;
-    auto advance = [&]() {
-      if (++slot == NS) {
-        slot = 0;
-        phase ^= 1u;
-      }
-    };
-    auto row_skip = [&](uint32_t& mid_slot) {
-      mbar_wait(full0 + 8 * slot, phase);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);
-      mid_slot = slot;
-      advance();
-    };
-    auto row_step = [&](double2 (&up)[NBO], double2 (&mid)[NBO], double2 (&dn)[NBO], uint32_t& mid_base,
-                        uint32_t& mid_slot, double* const (&jp)[NBO], int64_t ro) {
-      mbar_wait(full0 + 8 * slot, phase);
-      const uint32_t base = ring0 + slot * SB;
-#pragma unroll
-      for (int q = 0; q < NBO; ++q)
-        if (q < nown) dn[q] = lds2(base + poff[q]);
-      double lf[NBO], rt[NBO];
-#pragma unroll
-      for (int q = 0; q < NBO; ++q) {
-        if (q < nown) {
-          lf[q] = lds1(mid_base + poff[q] - 8);
-          rt[q] = lds1(mid_base + poff[q] + 16);
-        }
-      }
-      double2 e = make_double2(0.0, 0.0);
-      if (p.has_e) e = lds2(mid_base + eoff);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);
-      mid_base = base;
-      mid_slot = slot;
-      advance();
-      const double dga = sg * __dadd_rn(d0, __dmul_rn(p.lam, e.x)), dgb = sg * __dadd_rn(d0, __dmul_rn(p.lam, e.y));
-      const double dgaL = fma(wsel, dga, wone), dgbL = fma(wsel, dgb, wone);
-      const uint32_t xb = xb0 + xsel * XB;
-      double2 tile[NB];
-#pragma unroll
-      for (int q = 0; q < NBO; ++q) {
-        if (q < nown) {
-          const bool last = (half == 1) && (q == nown - 1);
-          const double oa = apply_refbits(last ? cuL : cu, last ? clL : cl, last ? dgaL : dga, last ? cdL : cd, up[q].x,
-                                          lf[q], mid[q].x, mid[q].y, dn[q].x);
-          const double ob = apply_refbits(last ? cuL : cu, last ? clL : cl, last ? dgbL : dgb, last ? cdL : cd, up[q].y,
-                                          mid[q].x, mid[q].y, rt[q], dn[q].y);
-          const double2 v = make_double2(oa, ob);
-          if (!last || lastkind == 0) __stcs(reinterpret_cast<double2*>(jp[q] + ro), v);
-          sts2(xb + (uint32_t)(blk0 + q) * 512 + xlane, v);
-        }
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(barid) : "memory");  // both halves' tiles of this row are in the buffer
-#pragma unroll
-      for (int I = 0; I < NB; ++I) tile[I] = lds2(xb + (uint32_t)I * 512 + xlane);
-      xsel ^= 1u;
-      // this half's Gram blocks, in blk_index order
-#pragma unroll
-      for (int I = 0; I < NB; ++I)
-#pragma unroll
-        for (int J = I; J < NB; ++J) {
-          const int b = blk_index(NB, I, J);
-          if (b < GH0) {
-            if (half == 0) {
-              dmma(acc[b][0], acc[b][1], tile[I].x, tile[J].x);
-              dmma(acc[b][0], acc[b][1], tile[I].y, tile[J].y);
-            }
-          } else {
-            if (half == 1) {
-              dmma(acc[b - GH0][0], acc[b - GH0][1], tile[I].x, tile[J].x);
-              dmma(acc[b - GH0][0], acc[b - GH0][1], tile[I].y, tile[J].y);
-            }
-          }
-        }
-    };
-    for (int64_t task = blockIdx.x; task < ntask; task += gridDim.x) {
-      const int strip = (int)(task / ntj), tj = (int)(task - (int64_t)strip * ntj);
-      const int i0 = strip * TI, i1 = min(i0 + TI, p.rows);
-      const bool active = tj * TJ + 8 * seg < m;
-      double2 ra[NBO], rb[NBO], rc[NBO];
-      {  // row i0 - 1
-        mbar_wait(full0 + 8 * slot, phase);
-        const uint32_t base = ring0 + slot * SB;
-#pragma unroll
-        for (int q = 0; q < NBO; ++q)
-          if (q < nown) ra[q] = lds2(base + poff[q]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-        advance();
-      }
-      uint32_t mid_base, mid_slot;
-      {  // row i0
-        mbar_wait(full0 + 8 * slot, phase);
-        mid_base = ring0 + slot * SB;
-        mid_slot = slot;
-#pragma unroll
-        for (int q = 0; q < NBO; ++q)
-          if (q < nown) rb[q] = lds2(mid_base + poff[q]);
-        advance();
-      }
-      const int j = tj * TJ + 8 * seg + 2 * t;
-      double* jp[NBO];
-#pragma unroll
-      for (int q = 0; q < NBO; ++q) jp[q] = JV + (int64_t)(8 * (blk0 + (q < nown ? q : 0)) + g) * p.ldjv + j;
-      int64_t ro = (int64_t)i0 * m;
-      int i = i0;
-      if (active) {
-        while (true) {
-          row_step(ra, rb, rc, mid_base, mid_slot, jp, ro);
-          ro += m;
-          if (++i == i1) break;
-          row_step(rb, rc, ra, mid_base, mid_slot, jp, ro);
-          ro += m;
-          if (++i == i1) break;
-          row_step(rc, ra, rb, mid_base, mid_slot, jp, ro);
-          ro += m;
-          if (++i == i1) break;
-        }
-      } else {
-        for (; i < i1; ++i) row_skip(mid_slot);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * mid_slot);  // row i1 was only ever a dn row
-    }
-  }
-  // CTA sum in warp order: warp (seg, half) adds its accumulators to its half's blocks
-  for (int e = threadIdx.x; e < NBLK * 64; e += NT) red[e] = 0.0;
-  __syncthreads();
-  for (int w = 0; w < CWARPS; ++w) {
-    if (warp == w) {
-      const int nmine = half ? NBLK - GH0 : GH0, first = half ? GH0 : 0;
-#pragma unroll
-      for (int b = 0; b < NACC; ++b) {
-        if (b < nmine) {
-          double2* q = reinterpret_cast<double2*>(red + (first + b) * 64 + lane * 2);
-          double2 v = *q;
-          v.x += acc[b][0];
-          v.y += acc[b][1];
-          *q = v;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  constexpr int NE = NBLK * 64;
-  double* mine = partials + (int64_t)blockIdx.x * NE;
-  for (int e = threadIdx.x; e < NE; e += NT) mine[e] = red[e];
-  __threadfence();
-  if (!grid_arrive_last(ticket)) return;
-  const int nb = gridDim.x;
-  for (int e = threadIdx.x; e < NE; e += NT) {
-    double sum = 0.0;
-    for (int b = 0; b < nb; ++b) sum += __ldcg(partials + (int64_t)b * NE + e);
-    Gout[e] = sum;
-  }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1397,60 +1136,13 @@ int gnk_cholqr_try(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows,
   return 1;
 }
 
-template <int NB, int RU, int SW>
-int run_stencil_gram_pair(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu,
-                          const double* d_V, int64_t ldv, int v_cols, int k, const double* d_r, double sign, double* d_JV,
-                          int64_t ldjv, double sign_a, double* d_out, cudaStream_t st) {
-  if (int rc = ensure_scratch(ctx, st)) return rc;
-  double* base = ctx->d_cholqr;
-  constexpr int PW = 8 * SW + 8, TJ = 8 * SW;
-  const int stored_rows = lay->rows + 2 * lay->halo;
-  CUtensorMap tmV, tmY, tmE;
-  if (int rc = make_column_map(&tmV, d_V, lay->m, stored_rows, ldv, v_cols, 8 * NB, PW)) return rc;
-  if (int rc = make_column_map(&tmY, d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
-  const bool has_e = prm->lam != 0.0;
-  if (int rc = make_column_map(&tmE, has_e ? d_expu : d_r, lay->m, stored_rows, lay->ld, 1, 1, PW)) return rc;
-  auto kern = stencil_gram_pair_kernel<NB, SW>;
-  constexpr int SB = sg_slot_bytes<NB, SW>();
-  constexpr int XB = NB * 512;
-  constexpr int NS = ((200 * 1024 - 2 * SW * XB) / SB) < 16 ? ((200 * 1024 - 2 * SW * XB) / SB) : 16;
-  constexpr int dyn = NS * SB + 2 * SW * XB;
-  static bool attr_set[64] = {false};
-  if (!attr_set[ctx->device & 63]) {
-    GNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    attr_set[ctx->device & 63] = true;
-  }
-  const int ntj = (lay->m + TJ - 1) / TJ;
-  int TI = 64;
-  while (TI > 8 && (int64_t)ntj * ceil_div(lay->rows, TI) < 6LL * ctx->sm_count) TI >>= 1;
-  const int64_t ntask = (int64_t)ntj * ceil_div(lay->rows, TI);
-  const int ctas = (int)(ntask < ctx->sm_count ? ntask : ctx->sm_count);
-  StencilPanel p{lay->m, lay->rows, k, has_e ? 1 : 0, ldjv, prm->c_lap, prm->c_adv, prm->lam, sign};
-  GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), kern, dim3(ctas), dim3(32 * (2 * SW + 1)), (size_t)dyn, st, tmV, tmY, tmE,
-                      p, TI, d_JV, base + CQ_PART, ctx->d_tickets + TK_CHOLQR, base + CQ_LOCAL));
-  GNK_LAUNCH_CHECK(ctx);
-  return cholqr_tail<NB, RU>(ctx, d_JV, ldjv, lay->n_own, k, d_r + lay->off, sign_a, d_out, st);
-}
-
-// consumer warps of the fused kernel: 8 (64-point tiles) by default; GNK_SG_CW=10 selects 80-point tiles (development)
+// 8 consumer warps (64-point tiles).  Measured and not kept (profiles/r02_pair_kernel_experiment.txt):
+// 10 consumer warps with 80-point tiles (no gain), two warps per segment that split the column blocks (slower: the
+// kernel is power-/FP64-bound, more FP64 work in flight lowers the SM clock under the power cap).
 template <int NB, int RU>
 int run_stencil_gram(gnk_ctx* ctx, const gnk_layout* lay, const gnk_bratu* prm, const double* d_expu, const double* d_V,
                      int64_t ldv, int v_cols, int k, const double* d_r, double sign, double* d_JV, int64_t ldjv,
                      double sign_a, double* d_out, cudaStream_t st) {
-  static const int cw = getenv("GNK_SG_CW") ? atoi(getenv("GNK_SG_CW")) : 8;
-  // GNK_SG_PAIR: 0 = one warp per segment (the kernel above), 6 / 8 = two warps per segment with 6 / 8 segments per tile
-  static const int pair = getenv("GNK_SG_PAIR") ? atoi(getenv("GNK_SG_PAIR")) : 0;
-  if constexpr (NB >= 2) {
-    if (pair == 6)
-      return run_stencil_gram_pair<NB, RU, 6>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a,
-                                              d_out, st);
-    if (pair == 8)
-      return run_stencil_gram_pair<NB, RU, 8>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a,
-                                              d_out, st);
-  }
-  if (cw == 10)
-    return run_stencil_gram_cw<NB, RU, 10>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a,
-                                           d_out, st);
   return run_stencil_gram_cw<NB, RU, 8>(ctx, lay, prm, d_expu, d_V, ldv, v_cols, k, d_r, sign, d_JV, ldjv, sign_a, d_out,
                                         st);
 }
