@@ -235,10 +235,11 @@ inline int pick_tr(const gnk_ctx* ctx, int gx, int rows, int mult) {
 }
 
 // the fused residual kernel carries exp() and a block reduction per strip: measured best with the tallest strip that
-// still gives every SM two CTAs
+// still gives every SM six 128-thread CTAs (two were enough to fill the machine at 4096^2 but left the 512-row slabs
+// of an 8-GPU run at 14 warps per SM: 34 us for 10 us of traffic)
 inline int pick_tr_tall(const gnk_ctx* ctx, int gx, int rows) {
   int tr = 32;
-  while (tr > 1 && (int64_t)gx * ceil_div(rows, tr) < 2LL * ctx->sm_count) tr >>= 1;
+  while (tr > 2 && (int64_t)gx * ceil_div(rows, tr) < 6LL * ctx->sm_count) tr >>= 1;
   return tr;
 }
 

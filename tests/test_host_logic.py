@@ -458,3 +458,53 @@ def test_reference_modules_pin_the_oracle():
     po = orc.gnk(o.make_res(y), u0, o.make_jac(), max_iter=15, callback=lambda x, nfev, cg_iter: xo.append(x.copy()))
     assert (po["nit"], po["nfev"], po["njev"]) == (out.nit, out.nrev, out.njev)
     assert max(rel(a, b) for a, b in zip(xo, xs)) < 1e-11
+
+
+def test_speculative_expansion_changes_nothing(g, monkeypatch, capsys):
+    """The basis expansion enqueued behind the first Armijo trial (GNK_SPECULATE, default on) against the expansion
+    after the trial was judged: same iterates bit for bit, same counters, same messages -- on a run with accepted first
+    trials (Bratu), on one with REJECTED first trials (the speculated expansion must be dropped and redone), with
+    restarts, with a breakdown (the deferred flag travels through the second slot) and for every `version`."""
+    from gauss_newton_via_generalized_krylov_subspaces_b200 import rosenbrock_problem as rp
+    gd = Golden("bratu_g34")
+    pb = g.BratuPdeProblem(34, 5, 10)
+    res, jac = pb.make_res(gd["y"]), pb.make_jac()
+    lin = g.BratuPdeProblem(25, 5, 0)
+    gl = Golden("bratu_g25_linear")
+    lres, ljac = lin.make_res(gl["y"]), lin.make_jac()
+
+    def runs():
+        out = []
+        for version in ("res_old", "res_new", "jac_old_res_old", "jac_old_res_new"):
+            xs = []
+            o = g.gauss_newton_krylow(res, gd["u0"], jac, callback=lambda x, nfev, cg_iter: xs.append((np.array(x), nfev)),
+                                      max_iter=18, krylow_restart=7, version=version)
+            out.append((o.x, o.nit, o.nrev, o.njev, o.success, xs))
+        # a start far from the valley: several trials per iteration are rejected (Armijo halving)
+        x0 = np.full(1000, -1.5)
+        xs = []
+        o = g.gauss_newton_krylow(rp.res, x0, rp.jac, callback=lambda x, nfev, cg_iter: xs.append((np.array(x), nfev)),
+                                  max_iter=12)
+        assert o.nrev > o.nit + 1                      # halving happened
+        out.append((o.x, o.nit, o.nrev, o.njev, o.success, xs))
+        # breakdown at iteration 2 of the linear problem
+        xs = []
+        try:
+            o = g.gauss_newton_krylow(lres, gl["u0"], ljac, callback=lambda x, nfev, cg_iter: xs.append((np.array(x), nfev)),
+                                      max_iter=6)
+            out.append((o.x, o.nit, o.nrev, o.njev, o.success, xs))
+        except g.StepLengthConvergenceError:
+            out.append((None, None, None, None, None, xs))
+        return out, capsys.readouterr().out
+
+    monkeypatch.setenv("GNK_SPECULATE", "1")
+    a, msg_a = runs()
+    monkeypatch.setenv("GNK_SPECULATE", "0")
+    b, msg_b = runs()
+    assert msg_a == msg_b and "breakdown" in msg_a
+    for ra, rb in zip(a, b):
+        assert ra[1:5] == rb[1:5]
+        assert (ra[0] is None and rb[0] is None) or np.array_equal(ra[0], rb[0])
+        assert len(ra[5]) == len(rb[5])
+        for (xa, na), (xb, nb) in zip(ra[5], rb[5]):
+            assert na == nb and np.array_equal(xa, xb)
