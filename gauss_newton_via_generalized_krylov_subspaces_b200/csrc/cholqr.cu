@@ -501,16 +501,27 @@ __global__ void __launch_bounds__(FT) cholqr_factor1_kernel(const double* __rest
   if (ok) {
     Rs[i * GLD + l] = r;
     __syncthreads();  // also separates the row buffers of the two loops
-    t = block_tri_inverse(Rs, c, rowbuf);
-    // d0_i = sum_{m = i .. k-1} T[i][m] z[m],  z = R1[:k, k]  (warp i, lane m)
-    const double zl = (l < k) ? Rs[l * GLD + k] : 0.0;
-    const double d0 = warp_sum((l >= i && l < k) ? t * zl : 0.0);
-    if (l == 0 && i < k) d0g[i] = d0;
-    if (i == 0) {
-      const double z2 = warp_sum(zl * zl);
+    if (threadIdx.x < 32) {
+      // normal-equation solution by back substitution R1[:k,:k] d0 = z, z = R1[:k,k] (lane = row; once d0_j is known
+      // every row above subtracts R_ij d0_j) -- the explicit inverse T = R1^{-1} (c more block-wide steps with a
+      // barrier each) is formed only for the second CholeskyQR2 pass, which the default chain no longer runs
+      const bool row = l < k;
+      double z = row ? Rs[l * GLD + k] : 0.0;
+      const double rinv = row ? 1.0 / Rs[l * GLD + l] : 1.0;
+      const double z2 = warp_sum(z * z);
+      double d = 0.0;
+      for (int j = k - 1; j >= 0; --j) {
+        const double dj = __shfl_sync(0xffffffffu, z, j) * __shfl_sync(0xffffffffu, rinv, j);
+        if (l == j) d = dj;
+        if (l < j) z = fma(-Rs[l * GLD + j], dj, z);
+      }
+      if (row) d0g[l] = d;
       if (l == 0) aux[0] = z2;
     }
-    if (i < k) t *= sign;
+    if (method == 2) {
+      t = block_tri_inverse(Rs, c, rowbuf);
+      if (i < k) t *= sign;
+    }
   }
   Tg[i * TLD + l] = t;
   if (l < TLD - MAXC) Tg[i * TLD + MAXC + l] = 0.0;
@@ -557,7 +568,7 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
     return;
   }
   if (mode == 0) {
-    // refinement form: delta = T (T^T g), d = d0 + delta  (T carries the sign in its rows: sign^2 = 1)
+    // refinement form: delta = (R1^T R1)^{-1} g, d = d0 + delta
     double* gs = rowbuf;   // k + 1 values (2 * RB >= MAXC + 1)
     double* us = diag;
     __shared__ double dsum[2];
@@ -567,14 +578,28 @@ __global__ void __launch_bounds__(FT) cholqr_factor2_kernel(const double* __rest
       for (int r = 1; r < nparts; ++r) g += parts[(int64_t)r * pstride + threadIdx.x];
       gs[threadIdx.x] = g;
     }
-    R1s[i * GLD + l] = Tg[i * TLD + l];  // T
+    R1s[i * GLD + l] = R1g[i * MAXC + l];  // R1 (upper triangular)
     __syncthreads();
-    const double u = warp_sum((l <= i && i < k) ? R1s[l * GLD + i] * gs[l] : 0.0);   // u_i = sum_m T[m][i] g[m]
-    if (l == 0) us[i] = (i < k) ? u : 0.0;
-    __syncthreads();
-    const double delta = warp_sum((l >= i && l < k) ? R1s[i * GLD + l] * us[l] : 0.0);  // delta_i = sum_m T[i][m] u[m]
-    __syncthreads();
-    if (l == 0) us[i] = delta;
+    if (threadIdx.x < 32) {
+      // delta = (R1^T R1)^{-1} g by two triangular solves (lane = row): forward R1^T u = g, backward R1 delta = u.
+      // (sign^2 = 1: g = (sign A)^T rho already carries the sign, the Gram block of the A columns does not.)
+      const bool row = l < k;
+      const double rinv = row ? 1.0 / R1s[l * GLD + l] : 1.0;
+      double z = row ? gs[l] : 0.0, u = 0.0;
+      for (int j = 0; j < k; ++j) {
+        const double uj = __shfl_sync(0xffffffffu, z, j) * __shfl_sync(0xffffffffu, rinv, j);
+        if (l == j) u = uj;
+        if (l > j && row) z = fma(-R1s[j * GLD + l], uj, z);
+      }
+      z = u;
+      double dl_ = 0.0;
+      for (int j = k - 1; j >= 0; --j) {
+        const double dj = __shfl_sync(0xffffffffu, z, j) * __shfl_sync(0xffffffffu, rinv, j);
+        if (l == j) dl_ = dj;
+        if (l < j) z = fma(-R1s[l * GLD + j], dj, z);
+      }
+      if (row) us[l] = dl_;
+    }
     __syncthreads();
     if (threadIdx.x < 32) {
       const bool row = l < k;

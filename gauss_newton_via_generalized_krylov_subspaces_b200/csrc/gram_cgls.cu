@@ -44,7 +44,7 @@ struct Panel {
 };
 
 // G = P^T P for the panel P = [A | y] with NB column blocks of 8; lane (g, t) holds rows 2t, 2t+1 of column 8 I + g of
-// an 8-row group: both the A and the B fragment of the DMMAs (see cholqr.cu).  A warp owns 16 rows per step.
+// an 8-row group: both the A and the B fragment of the DMMAs (see cholqr.cu).  A warp owns 8 rows per step.
 template <int NB>
 __global__ void __launch_bounds__(WT, 1)
     gram_wide_kernel(Panel src, int64_t rows_per_cta, double* __restrict__ partials, unsigned int* ticket,
@@ -66,26 +66,40 @@ __global__ void __launch_bounds__(WT, 1)
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   int64_t limit = row0 + rows_per_cta;
   if (limit > src.n_rows) limit = src.n_rows;
-  for (int64_t r = row0 + 16 * warp; r < limit; r += 16 * WG) {
-    double2 v[NB][2];
+  // 8 rows per warp and step, the next step's rows already in flight (two register tiles): with a single tile the
+  // loads and the DMMAs of a warp alternated and the kernel ran at 0.33 of the HBM roofline (config 5, k <= 50)
+  constexpr int64_t STEP = 8 * WG;
+  auto load8 = [&](double2 (&v)[NB], int64_t r) {
+#pragma unroll
+    for (int I = 0; I < NB; ++I) {
+      const int64_t rr = r + 2 * t;
+      v[I] = (cp[I] != nullptr && rr < limit) ? __ldcs(reinterpret_cast<const double2*>(cp[I] + rr))
+                                              : make_double2(0.0, 0.0);
+    }
+  };
+  auto mma8 = [&](const double2 (&v)[NB]) {
 #pragma unroll
     for (int I = 0; I < NB; ++I)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int64_t rr = r + 8 * h + 2 * t;
-        v[I][h] = (cp[I] != nullptr && rr < limit) ? __ldcs(reinterpret_cast<const double2*>(cp[I] + rr))
-                                                   : make_double2(0.0, 0.0);
+      for (int J = I; J < NB; ++J) {
+        const int b = blk_index(NB, I, J);
+        dmma(acc[b][0], acc[b][1], v[I].x, v[J].x);
+        dmma(acc[b][0], acc[b][1], v[I].y, v[J].y);
       }
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int I = 0; I < NB; ++I)
-#pragma unroll
-        for (int J = I; J < NB; ++J) {
-          const int b = blk_index(NB, I, J);
-          dmma(acc[b][0], acc[b][1], v[I][h].x, v[J][h].x);
-          dmma(acc[b][0], acc[b][1], v[I][h].y, v[J][h].y);
-        }
+  };
+  {
+    double2 va[NB], vb[NB];
+    int64_t r = row0 + 8 * warp;
+    load8(va, r);
+    while (r < limit) {
+      load8(vb, r + STEP);
+      mma8(va);
+      r += STEP;
+      if (r >= limit) break;
+      load8(va, r + STEP);
+      mma8(vb);
+      r += STEP;
+    }
   }
   // CTA sum in warp order, CTA partial, last CTA adds the partials in CTA order (deterministic)
   for (int w = 0; w < WG; ++w) {
@@ -247,7 +261,7 @@ __global__ void __launch_bounds__(CT) gram_pcg_kernel(double* __restrict__ parts
 
 template <int NB>
 int launch_gram_wide(gnk_ctx* ctx, const Panel& src, double* scratch, cudaStream_t st) {
-  constexpr int64_t GRAN = 16 * WG;
+  constexpr int64_t GRAN = 8 * WG;
   int64_t ctas = ctx->sm_count;
   if (ctas * GRAN > src.n_rows) ctas = ceil_div(src.n_rows, GRAN);
   if (ctas < 1) ctas = 1;

@@ -123,7 +123,19 @@ __global__ void __launch_bounds__(TPB) normalize_kernel(const double* __restrict
   const double nrm = sqrt(ss);
   const int64_t nv = len >> 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // four independent 128-bit loads in flight per thread (one per iteration kept the kernel at 0.67 of the roofline:
+  // 4.8 MB in flight on the whole GPU), true divisions as in the reference (w /= norm, krylow.py:71)
+  for (; i + 3 * stride < nv; i += 4 * stride) {
+    double2 a = ld2(x + 2 * i), b = ld2(x + 2 * (i + stride)), c = ld2(x + 2 * (i + 2 * stride)),
+            d = ld2(x + 2 * (i + 3 * stride));
+    a.x /= nrm; a.y /= nrm; b.x /= nrm; b.y /= nrm; c.x /= nrm; c.y /= nrm; d.x /= nrm; d.y /= nrm;
+    st2(out + 2 * i, a);
+    st2(out + 2 * (i + stride), b);
+    st2(out + 2 * (i + 2 * stride), c);
+    st2(out + 2 * (i + 3 * stride), d);
+  }
+  for (; i < nv; i += stride) {
     double2 v = ld2(x + 2 * i);
     v.x = v.x / nrm;
     v.y = v.y / nrm;
