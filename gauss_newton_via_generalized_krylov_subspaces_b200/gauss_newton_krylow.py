@@ -37,7 +37,7 @@ _NB = _lib.GNK_MAX_BASIS
 _SC_LOSS = 2 * _NB + 8   # 2 doubles: sum(F^2) [, max|F|]
 _SC_CPREV = _SC_LOSS + 2  # sum(c_prev^2)
 _SC_FLAG = _SC_CPREV + 2   # int32 in a double slot: the deferred Krylov breakdown flag (krylow.dev_update)
-_SC_FLAG2 = _SC_CPREV + 3  # the same for a speculatively enqueued expansion (moved to _SC_FLAG when it is committed)
+_SC_FLAG2 = _SC_CPREV + 3  # second slot: an expansion writes its flag to the slot that is NOT pending, committing it flips
 _BLK = _SC_CPREV + 6
 _VERSIONS = ("res_old", "res_new", "jac_old_res_old", "jac_old_res_new")
 
@@ -308,7 +308,13 @@ def gauss_newton_krylow(
 
     JV = None
     jv_cap = 0
-    state = {"pending": False}  # pending: the last basis expansion left its breakdown flag unread (see below)
+    # pending: the last basis expansion left its breakdown flag unread (see below); fslot: the slot that holds it.  A new
+    # expansion always writes the OTHER slot, so neither a device copy nor a race with the read-back is needed.
+    state = {"pending": False, "fslot": _SC_FLAG}
+
+    def other_slot():
+        return _SC_FLAG2 if state["fslot"] == _SC_FLAG else _SC_FLAG
+
     defer_ok = ls_solver == "qr" and os.environ.get("GNK_DEFER_BREAKDOWN", "1") != "0"
 
     for iter in range(1, max_iter):
@@ -388,14 +394,14 @@ def gauss_newton_krylow(
                 if spec_ok and state["spec"] is None:
                     ev = rt.mark_event()       # the scalars of this trial are complete here ...
                     jac_new = prob.jacobian(x_trial, aux=aux[1])
-                    krylow.dev_expand_enqueue(*expansion_operands(jac_new), hx, ptr(blk, _SC_FLAG2))
+                    krylow.dev_expand_enqueue(*expansion_operands(jac_new), hx, ptr(blk, other_slot()))
                     state["spec"] = jac_new
                     state["vals"] = rt.read_at(blk, _BLK, ev)   # ... and are read while the expansion runs
                 else:
                     if state["spec"] is not None:
                         state["spec"] = False  # a later trial: the speculation belonged to a rejected one
                     state["vals"] = rt.read(blk, _BLK)
-                if state["pending"] and state["vals"][_SC_FLAG:_SC_FLAG + 1].view(np.int32)[0] != 0:
+                if state["pending"] and state["vals"][state["fslot"]:state["fslot"] + 1].view(np.int32)[0] != 0:
                     raise _DeferredBreakdown()
                 if ls_solver == "qr" and ls_refused(state["vals"], k):
                     raise _LeastSquaresRefused()
@@ -453,12 +459,12 @@ def gauss_newton_krylow(
         # defer the breakdown read-back unless this iteration is the last one or ends with a restart (the message
         # of :127 must appear before either)
         defer = defer_ok and iter + 1 < max_iter and iter % krylow_restart != 0
-        dflag = ptr(blk, _SC_FLAG) if defer else None
+        new_slot = other_slot()
+        dflag = ptr(blk, new_slot) if defer else None
         try:
             if speculated:
-                # the expansion was enqueued behind the accepted trial; its flag sits in the second slot and moves to
-                # the slot the next iteration inspects
-                blk[_SC_FLAG:_SC_FLAG + 1].copy_(blk[_SC_FLAG2:_SC_FLAG2 + 1], non_blocking=True)
+                # the expansion was enqueued behind the accepted trial; its flag sits in the other slot, which becomes
+                # the one the next iteration inspects
                 krylow.commit()
             elif version == "res_old":
                 krylow.dev_update(jac_ev, F_cur, hx, dflag)
@@ -473,6 +479,8 @@ def gauss_newton_krylow(
                     "Variable version must be in ['res_old','res_new','jac_old_res_old','jac_old_res_new']"
                 )
             state["pending"] = defer
+            if defer:
+                state["fslot"] = new_slot
         except GeneralizedKrylowSubspaceBreakdown:
             print(
                 f"Generalized krylow subspace breakdown at iteration = {iter}, basis.shape = ({prob.p_glob}, {krylow.k})"
