@@ -113,7 +113,7 @@ int ensure_gather(gnk_ctx* ctx, size_t bytes, cudaStream_t st) {
 // The residual, Gram-Schmidt dots and update-statistics kernels run the same protocol in their own last CTA
 // (p2p_tail_allreduce, common.cuh), so those reductions need no kernel of their own at all.
 // =================================================================================================
-inline size_t p2p_bytes(int nranks) { return p2p_halo_off(nranks, 2, 0); }
+inline size_t p2p_bytes(int nranks) { return p2p_hll_off(nranks, 2, 0); }
 
 // op: 0 sum, 1 max, 2 (sum, max) pair as in gnk_comm_allreduce, 3 no reduction: out receives the nranks x count stack
 __global__ void __launch_bounds__(1024) p2p_gather_kernel(void* const* __restrict__ peers, int rank, int nranks,

@@ -149,7 +149,9 @@ __device__ __forceinline__ unsigned int total_blocks() { return gridDim.x * grid
 // peer-memory mailboxes (comm.cu): layout and the device side of a gather, shared with the kernels that finish their
 // cross-rank reduction in their own last CTA (residual, Gram-Schmidt dots, update statistics)
 // Mailbox layout (bytes): [0, 4096) flags: u64 gather[16], u64 halo[2] at +1024;
-//                         gather data 2 x nranks x P2P_GMAX doubles; halo data 2 parities x 2 sides x P2P_HMAX doubles.
+//                         gather data 2 x nranks x P2P_GMAX doubles; halo data 2 parities x 2 sides x P2P_HMAX doubles;
+//                         2 x nranks x P2P_LLMAX 16-byte lines {lo, tag, hi, tag} of the in-kernel all-reduces;
+//                         2 parities x 2 sides x P2P_HMAX such lines for the halo rows pushed by normalize_halo_kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int P2P_MAXR = 16;
 constexpr int64_t P2P_GMAX = (int64_t)GNK_TSQR_MAX * GNK_TSQR_MAX;    // largest gather: one R triangle
@@ -163,6 +165,15 @@ __host__ __device__ inline size_t p2p_gather_off(int nranks, int parity, int r) 
 __host__ __device__ inline size_t p2p_halo_off(int nranks, int parity, int side) {
   return P2P_FLAG_BYTES + sizeof(double) * (size_t)(2 * nranks * P2P_GMAX) +
          sizeof(double) * (size_t)((parity * 2 + side) * P2P_HMAX);
+}
+// flag-in-data lines of the in-kernel all-reduces (p2p_tail_allreduce): 16 bytes per double, after the halo slots
+constexpr int P2P_LLMAX = 1024;
+__host__ __device__ inline size_t p2p_ll_off(int nranks, int parity, int r) {
+  return p2p_halo_off(nranks, 2, 0) + 16 * (size_t)((parity * nranks + r) * P2P_LLMAX);
+}
+// the same lines for the halo rows pushed by normalize_halo_kernel (vector_ops.cu): 2 parities x 2 sides x P2P_HMAX
+__host__ __device__ inline size_t p2p_hll_off(int nranks, int parity, int side) {
+  return p2p_ll_off(nranks, 2, 0) + 16 * (size_t)((parity * 2 + side) * P2P_HMAX);
 }
 
 struct gnk_p2p_dev {        // kernel argument; peers == nullptr: single rank or NCCL path, nothing to do
@@ -208,35 +219,48 @@ __device__ __forceinline__ double ld_volatile(const double* p) {
   return v;
 }
 
-// Cross-rank reduction of vals[0..count) (count, nranks <= blockDim.x), executed by ALL threads of ONE CTA -- the
-// CTA that has just written this rank's values (make them visible with a __syncthreads first).  Same protocol and
-// same rank-ordered arithmetic as p2p_gather_kernel (comm.cu): store into every peer's mailbox over NVLink, fence,
-// raise the flags, wait for the peers' flags, reduce out of local memory.  op: 0 sum, 1 max, 2 (sum, max) pair.
+// Cross-rank reduction of vals[0..count) (count <= blockDim.x, count <= P2P_LLMAX), executed by ALL threads of ONE
+// CTA -- the CTA that has just written this rank's values (make them visible with a __syncthreads first).  Same
+// rank-ordered arithmetic as p2p_gather_kernel (comm.cu), but a flag-in-data protocol instead of data + fence + flag:
+// every double travels as ONE 16-byte store {lo, seq32, hi, seq32} into the peer's mailbox, and the receiver polls the
+// line itself until both tags carry this collective's number (each 8-byte half of the line is written atomically, so a
+// line whose two tags match holds both halves of the value).  No __threadfence_system (a full NVLink round trip), no
+// separate flag hop, no block barrier: the cost is one one-way store latency plus the ranks' skew.  Lines are
+// double-buffered on the parity of the sequence number like the other slots (a rank is never more than one collective
+// ahead of a peer), and a tag can only match a stale line after 2^32 - 1 collectives.  op: 0 sum, 1 max, 2 (sum, max).
+__device__ __forceinline__ void st_ll(void* p, double v, unsigned tag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ double ld_ll(const void* p, unsigned tag) {
+  unsigned lo, t1, hi, t2;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(p) : "memory");
+  if (t1 != tag || t2 != tag) {
+    const unsigned long long t0 = global_ns();
+    do {
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(p) : "memory");
+      if (global_ns() - t0 > P2P_TIMEOUT_NS) __trap();  // a peer that never arrives must not hang the GPU
+    } while (t1 != tag || t2 != tag);
+  }
+  return __hiloint2double((int)hi, (int)lo);
+}
 __device__ __forceinline__ void p2p_tail_allreduce(const gnk_p2p_dev& pd, double* vals, int count, int op) {
   const int t = threadIdx.x;
+  if (t >= count) return;
   const int parity = (int)(pd.seq & 1ull);
-  if (t < count) {
-    const double v = vals[t];
-    for (int r = 0; r < pd.nranks; ++r)
-      reinterpret_cast<double*>(static_cast<char*>(pd.peers[r]) + p2p_gather_off(pd.nranks, parity, pd.rank))[t] = v;
+  const unsigned tag = (unsigned)(pd.seq % 0xFFFFFFFFull) + 1u;  // never 0: the mailbox starts zeroed
+  const double v = vals[t];
+  for (int r = 0; r < pd.nranks; ++r)
+    st_ll(static_cast<char*>(pd.peers[r]) + p2p_ll_off(pd.nranks, parity, pd.rank) + 16 * (size_t)t, v, tag);
+  const char* mine = static_cast<const char*>(pd.peers[pd.rank]);
+  const bool is_max = (op == 1) || (op == 2 && t == 1);
+  double a = ld_ll(mine + p2p_ll_off(pd.nranks, parity, 0) + 16 * (size_t)t, tag);
+  for (int r = 1; r < pd.nranks; ++r) {
+    const double b = ld_ll(mine + p2p_ll_off(pd.nranks, parity, r) + 16 * (size_t)t, tag);
+    a = is_max ? fmax(a, b) : a + b;
   }
-  __threadfence_system();
-  __syncthreads();
-  char* mine = static_cast<char*>(pd.peers[pd.rank]);
-  if (t < pd.nranks) {
-    st_release_sys(reinterpret_cast<unsigned long long*>(pd.peers[t]) + pd.rank, pd.seq);
-    wait_flag(reinterpret_cast<const unsigned long long*>(mine) + t, pd.seq);
-  }
-  __syncthreads();
-  if (t < count) {
-    double a = ld_volatile(reinterpret_cast<const double*>(mine + p2p_gather_off(pd.nranks, parity, 0)) + t);
-    const bool is_max = (op == 1) || (op == 2 && t == 1);
-    for (int r = 1; r < pd.nranks; ++r) {
-      const double b = ld_volatile(reinterpret_cast<const double*>(mine + p2p_gather_off(pd.nranks, parity, r)) + t);
-      a = is_max ? fmax(a, b) : a + b;
-    }
-    vals[t] = a;
-  }
+  vals[t] = a;
 }
 
 // One row of sign * (M v) or sign * (M^T v), M = L + alpha D + lam diag(e^u), in the order scipy uses for

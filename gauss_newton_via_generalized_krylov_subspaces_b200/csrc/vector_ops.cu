@@ -143,89 +143,71 @@ __global__ void __launch_bounds__(TPB) normalize_kernel(const double* __restrict
   }
 }
 
-// normalize fused with the halo exchange of the column it writes (multi-GPU, peer mailboxes attached): the CTAs that
-// write the first / last `cnt` owned doubles also store them into the lower / upper neighbour's mailbox (plain stores
-// over NVLink); the CTA that arrives last -- every store of this rank is then fenced -- raises this rank's flag in both
-// neighbours' mailboxes, waits for theirs, and copies the two received pieces into the halo rows of `out`.  Same
-// protocol, slots and sequence numbers as p2p_halo_kernel (comm.cu); one kernel and one launch gap fewer per outer
-// iteration.  On a breakdown nothing is written but the flags are still exchanged, so the sequence stays in step.
+// normalize fused with the halo exchange of the column it writes (multi-GPU, peer mailboxes attached): the threads that
+// write the first / last `cnt` owned doubles also push them into the lower / upper neighbour's mailbox over NVLink, as
+// 16-byte flag-in-data lines {lo, tag, hi, tag} (st_ll, common.cuh); the first HALO_RECV CTAs then poll the lines the
+// neighbours push into THIS rank's mailbox and write them into the halo rows of `out`.  No system-scope fence, no flag
+// hop, no grid-wide ticket and no single-CTA copy (round-2 history: data + fence + flag + one CTA copying 2 x 64 KB
+// cost 15-17 us per outer iteration at 8 GPUs on top of the 5 us of streaming): a line is complete when both tags
+// carry this exchange's number.  Lines are double-buffered on the parity of the exchange number; a rank can be at most
+// one exchange ahead of its neighbour because it cannot finish exchange s without the neighbour's lines of s.
+// A breakdown (max|w| <= atol) is decided from the all-reduced statistics, identically on every rank: nobody pushes
+// and nobody waits.  A receiving CTA may spin until the neighbour's kernel has started; the neighbour's progress never
+// depends on this rank's normalize kernel, so this cannot deadlock, and ld_ll traps after P2P_TIMEOUT_NS.
 struct HaloPush {
   void* const* peers;
   int rank, nranks, has_lo, has_hi;
   int64_t off, rows_m, cnt;  // first owned double, owned doubles, doubles per message (depth * m)
   unsigned long long seq;
 };
+constexpr int HALO_RECV = 32;
 __global__ void __launch_bounds__(TPB) normalize_halo_kernel(const double* __restrict__ x, int64_t len,
                                                               const double* __restrict__ stats, double atol,
-                                                              double* __restrict__ out, int32_t* flag, HaloPush hp,
-                                                              unsigned int* ticket) {
+                                                              double* __restrict__ out, int32_t* flag, HaloPush hp) {
   pdl_begin();
   const double ss = stats[0], mx = stats[1];
   const bool bad = (mx <= atol);
   if (blockIdx.x == 0 && threadIdx.x == 0) *flag = bad ? 1 : 0;
-  const int parity = (int)(hp.seq & 1ull);
-  bool remote = false;
-  if (!bad) {
-    const double nrm = sqrt(ss);
-    double* lo_dst = hp.has_lo ? reinterpret_cast<double*>(static_cast<char*>(hp.peers[hp.rank - 1]) +
-                                                            p2p_halo_off(hp.nranks, parity, 1))
-                               : nullptr;
-    double* hi_dst = hp.has_hi ? reinterpret_cast<double*>(static_cast<char*>(hp.peers[hp.rank + 1]) +
-                                                            p2p_halo_off(hp.nranks, parity, 0))
-                               : nullptr;
-    const int64_t lo_end = hp.off + hp.cnt, hi_beg = hp.off + hp.rows_m - hp.cnt, hi_end = hp.off + hp.rows_m;
-    const int64_t nv = len >> 1;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-      double2 v = ld2(x + 2 * i);
-      v.x = v.x / nrm;
-      v.y = v.y / nrm;
-      st2(out + 2 * i, v);
-      const int64_t e = 2 * i;  // off, cnt and rows_m are even: a pair never straddles a piece
-      if (lo_dst && e >= hp.off && e < lo_end) {
-        st2(lo_dst + (e - hp.off), v);
-        remote = true;
-      }
-      if (hi_dst && e >= hi_beg && e < hi_end) {
-        st2(hi_dst + (e - hi_beg), v);
-        remote = true;
-      }
-    }
-    // this thread's remote stores are visible system-wide before the CTA takes its ticket (only the few border threads
-    // pay for the system-scope fence)
-    if (remote) __threadfence_system();
-  }
-  if (!grid_arrive_last(ticket)) return;
-  char* mine = static_cast<char*>(hp.peers[hp.rank]);
-  const unsigned long long* myflags = reinterpret_cast<const unsigned long long*>(mine + 1024);
-  if (threadIdx.x == 0 && hp.has_lo) {
-    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(hp.peers[hp.rank - 1]) + 1024) + 1, hp.seq);
-    wait_flag(myflags + 0, hp.seq);
-  }
-  if (threadIdx.x == 32 && hp.has_hi) {
-    st_release_sys(reinterpret_cast<unsigned long long*>(static_cast<char*>(hp.peers[hp.rank + 1]) + 1024) + 0, hp.seq);
-    wait_flag(myflags + 1, hp.seq);
-  }
-  __syncthreads();
   if (bad) return;
-  // The received rows were written by the peers BEFORE their flags (release) and are read after the acquire above;
-  // .cg loads (L2, never a stale L1 line), 128 bits wide and four in flight per thread: the 2 x 64 KB copy by one CTA
-  // took ~45 us with one 8-byte volatile load at a time (measured at 8 GPUs: normalize 51 us instead of 8)
-  for (int side = 0; side < 2; ++side) {
-    if (!(side == 0 ? hp.has_lo : hp.has_hi)) continue;
-    const double2* g = reinterpret_cast<const double2*>(mine + p2p_halo_off(hp.nranks, parity, side));
-    double2* dst = reinterpret_cast<double2*>(out + (side == 0 ? hp.off - hp.cnt : hp.off + hp.rows_m));
-    const int64_t nv2 = hp.cnt >> 1;
-    int64_t i = threadIdx.x;
-    for (; i + 3 * (int64_t)blockDim.x < nv2; i += 4 * (int64_t)blockDim.x) {
-      const double2 a = __ldcg(g + i), b = __ldcg(g + i + blockDim.x), c = __ldcg(g + i + 2 * blockDim.x),
-                    d = __ldcg(g + i + 3 * blockDim.x);
-      dst[i] = a;
-      dst[i + blockDim.x] = b;
-      dst[i + 2 * blockDim.x] = c;
-      dst[i + 3 * blockDim.x] = d;
+  const int parity = (int)(hp.seq & 1ull);
+  const unsigned tag = (unsigned)(hp.seq % 0xFFFFFFFFull) + 1u;
+  const double nrm = sqrt(ss);
+  // my first rows become the lower neighbour's upper halo (its side 1), my last rows the upper neighbour's side 0
+  char* lo_dst = hp.has_lo ? static_cast<char*>(hp.peers[hp.rank - 1]) + p2p_hll_off(hp.nranks, parity, 1) : nullptr;
+  char* hi_dst = hp.has_hi ? static_cast<char*>(hp.peers[hp.rank + 1]) + p2p_hll_off(hp.nranks, parity, 0) : nullptr;
+  const int64_t lo_end = hp.off + hp.cnt, hi_beg = hp.off + hp.rows_m - hp.cnt, hi_end = hp.off + hp.rows_m;
+  const int64_t nv = len >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const int64_t e = 2 * i;  // off, cnt and rows_m are even: a pair never straddles a piece
+    // the halo rows that a neighbour fills are written by the receiving CTAs below and by nobody else
+    if ((lo_dst && e >= hp.off - hp.cnt && e < hp.off) || (hi_dst && e >= hi_end && e < hi_end + hp.cnt)) continue;
+    double2 v = ld2(x + 2 * i);
+    v.x = v.x / nrm;
+    v.y = v.y / nrm;
+    st2(out + 2 * i, v);
+    if (lo_dst && e >= hp.off && e < lo_end) {
+      st_ll(lo_dst + 16 * (e - hp.off), v.x, tag);
+      st_ll(lo_dst + 16 * (e - hp.off + 1), v.y, tag);
     }
-    for (; i < nv2; i += blockDim.x) dst[i] = __ldcg(g + i);
+    if (hi_dst && e >= hi_beg && e < hi_end) {
+      st_ll(hi_dst + 16 * (e - hi_beg), v.x, tag);
+      st_ll(hi_dst + 16 * (e - hi_beg + 1), v.y, tag);
+    }
+  }
+  if (blockIdx.x >= HALO_RECV) return;
+  const char* mine = static_cast<const char*>(hp.peers[hp.rank]);
+  const int64_t pairs = hp.cnt >> 1;
+  const int64_t rstride = (int64_t)(gridDim.x < HALO_RECV ? gridDim.x : HALO_RECV) * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < 2 * pairs; p += rstride) {
+    const int side = p >= pairs ? 1 : 0;
+    if (!(side == 0 ? hp.has_lo : hp.has_hi)) continue;
+    const int64_t j = p - side * pairs;
+    const char* line = mine + p2p_hll_off(hp.nranks, parity, side) + 32 * j;
+    double2 v;
+    v.x = ld_ll(line, tag);
+    v.y = ld_ll(line + 16, tag);
+    st2(out + (side == 0 ? hp.off - hp.cnt : hp.off + hp.rows_m) + 2 * j, v);
   }
 }
 
@@ -473,9 +455,13 @@ int gnk_normalize_halo(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, c
   GNK_REQUIRE(ctx && lay && d_x && d_stats && d_out && d_flag, "gnk_normalize_halo: null argument");
   const int depth = lay->halo;
   const int64_t cnt = (int64_t)depth * lay->m;
-  const bool fused = ctx->nranks > 1 && ctx->p2p_ready && ctx->p2p_fused && lay->m > 0 && depth >= 1 &&
-                     depth <= lay->rows && cnt <= P2P_HMAX && (lay->ld & 1) == 0 && (lay->off & 1) == 0 &&
-                     (cnt & 1) == 0 && (lay->n_own & 1) == 0;
+  // The fused kernel and the stand-alone exchange (comm.cu) use different wire formats, so the choice must come out
+  // the same on every rank: it depends on the row length and the halo depth only, never on this rank's slab.
+  const bool fused = ctx->nranks > 1 && ctx->p2p_ready && ctx->p2p_fused && lay->m > 0 && (lay->m & 1) == 0 &&
+                     depth >= 1 && cnt <= P2P_HMAX;
+  if (fused)
+    GNK_REQUIRE(depth <= lay->rows && (lay->ld & 1) == 0 && (lay->off & 1) == 0 && (lay->n_own & 1) == 0,
+                "gnk_normalize_halo: slab layout (an even row length implies even off / n_own / ld; depth <= rows)");
   if (!fused) {
     if (int rc = gnk_normalize(ctx, lay, d_x, d_stats, atol, d_out, d_flag, stream)) return rc;
     if (ctx->nranks > 1 && lay->m > 0) return gnk_comm_halo_exchange(ctx, lay, d_out, depth, stream);
@@ -485,7 +471,7 @@ int gnk_normalize_halo(gnk_ctx* ctx, const gnk_layout* lay, const double* d_x, c
               ++ctx->p2p_hseq};
   int grid = stream_grid(ctx, lay->ld / 2, 8);
   GNK_CUDA(gnk_launch(gnk_pdl_for(lay->n_own), normalize_halo_kernel, dim3(grid), dim3(TPB), 0, (cudaStream_t)stream, d_x, lay->ld, d_stats, atol,
-                      d_out, d_flag, hp, ctx->d_tickets + TK_NORMALIZE));
+                      d_out, d_flag, hp));
   GNK_LAUNCH_CHECK(ctx);
   return 0;
 }
