@@ -136,9 +136,9 @@ class GeneralizedKrylowSubspace:
         fp = ptr(self.flag) if flag_ptr is None else flag_ptr
         with rt.mark("normalize", 16.0 * n):
             if halo_exchange is not None:
-                # the one halo exchange of an outer iteration rides in the normalisation kernel (border CTAs store into
-                # the neighbours' mailboxes).  A breakdown leaves column k unwritten; the flags are exchanged anyway,
-                # which keeps every rank in the same sequence of collectives
+                # the one halo exchange of an outer iteration rides in the normalisation kernel (border threads push
+                # into the neighbours' mailboxes, 32 CTAs receive).  A breakdown leaves column k unwritten on every rank
+                # alike: it is decided from the all-reduced statistics, so nobody pushes and nobody waits
                 _lib.check(lib.gnk_normalize_halo(rt.ctx, C.byref(self.lay), ptr(self.w), ptr(self.stats), 1e-8,
                                                   ptr(new), fp, rt.stream), "gnk_normalize_halo")
             else:
