@@ -49,6 +49,8 @@ SIGNATURES = {
     "gnk_destroy": (_I, [_P]),
     "gnk_sm_count": (_I, [_P]),
     "gnk_launch_count": (_L, [_P]),
+    "gnk_scalars_fetch": (_I, [_P, _P, _I, _P, _P]),
+    "gnk_scalars_wait": (_I, [_P]),
     "gnk_bratu_residual": (_I, [_P, _LP, _BP, _P, _P, _P, _P, _I, _P, _P]),
     "gnk_stencil_apply": (_I, [_P, _LP, _BP, _P, _P, _L, _I, _D, _I, _P, _L, _L, _P]),
     "gnk_stencil_normal_diag": (_I, [_P, _LP, _BP, _P, _P, _P]),

@@ -63,6 +63,8 @@ int gnk_destroy(gnk_ctx* ctx) {
   if (ctx->d_cholqr) cudaFree(ctx->d_cholqr);
   if (ctx->d_gramw) cudaFree(ctx->d_gramw);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->fetch_stream) cudaStreamDestroy(ctx->fetch_stream);
+  if (ctx->fetch_event) cudaEventDestroy(ctx->fetch_event);
   delete ctx;
   return 0;
 }
@@ -70,5 +72,28 @@ int gnk_destroy(gnk_ctx* ctx) {
 int gnk_sm_count(gnk_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int64_t gnk_launch_count(gnk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// The scalar read-back of an outer iteration (gnk_b200.h): the copy waits for the work enqueued on `stream` so far and
+// runs on the context's own copy stream, so kernels enqueued on `stream` AFTER this call keep the device busy while the
+// host sits in gnk_scalars_wait.  Two driver calls and one wait instead of an event, a stream switch, a tensor copy and
+// a stream synchronisation through the framework (~25 us of host time per outer iteration in the latency regime).
+int gnk_scalars_fetch(gnk_ctx* ctx, const double* d_src, int count, double* h_dst, void* stream) {
+  GNK_REQUIRE(ctx && d_src && h_dst && count >= 1, "gnk_scalars_fetch: bad argument");
+  if (!ctx->fetch_stream) {
+    GNK_CUDA(cudaSetDevice(ctx->device));
+    GNK_CUDA(cudaStreamCreateWithFlags(&ctx->fetch_stream, cudaStreamNonBlocking));
+    GNK_CUDA(cudaEventCreateWithFlags(&ctx->fetch_event, cudaEventDisableTiming));
+  }
+  GNK_CUDA(cudaEventRecord(ctx->fetch_event, (cudaStream_t)stream));
+  GNK_CUDA(cudaStreamWaitEvent(ctx->fetch_stream, ctx->fetch_event, 0));
+  GNK_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->fetch_stream));
+  return 0;
+}
+
+int gnk_scalars_wait(gnk_ctx* ctx) {
+  GNK_REQUIRE(ctx && ctx->fetch_stream, "gnk_scalars_wait: no fetch in flight");
+  GNK_CUDA(cudaStreamSynchronize(ctx->fetch_stream));
+  return 0;
+}
 
 }  // extern "C"

@@ -43,6 +43,9 @@ struct gnk_ctx {
   double* d_cholqr = nullptr;
   double* d_gramw = nullptr;          // wide Gram matrix scratch of gnk_gram_cgls (gram_cgls.cu)
   int ls_method = 0;                  // gnk_tsqr_ls_method: 0 automatic, 1 Householder TSQR only
+  // gnk_scalars_fetch / gnk_scalars_wait (api.cu): the copy stream and event of the scalar read-back
+  cudaStream_t fetch_stream = nullptr;
+  cudaEvent_t fetch_event = nullptr;
 };
 
 constexpr int GNK_PARTIALS = 1 << 19;  // doubles (4 MiB)

@@ -39,6 +39,10 @@ class Runtime:
         self.fused_reductions = False  # gnk_bratu_residual / gnk_cgs_dots / gnk_cgs_update reduce over the ranks themselves
         self._pinned = torch.empty(4096, dtype=torch.float64, pin_memory=True)
         self._pinned_np = self._pinned.numpy()
+        self._pinned_ptr = self._pinned.data_ptr()
+        self._pinned2 = torch.empty(1024, dtype=torch.float64, pin_memory=True)
+        self._pinned2_np = self._pinned2.numpy()
+        self._pinned2_ptr = self._pinned2.data_ptr()
         self._pinned_i = torch.empty(16, dtype=torch.int32, pin_memory=True)
         self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         self._attach_comm_if_distributed()
@@ -82,13 +86,13 @@ class Runtime:
     # -- helpers -----------------------------------------------------------------------------------
     @property
     def stream(self):
-        """torch's current stream on this device as a cudaStream_t.  Asked for at every launch, so it goes through the
-        raw-handle query (0.2 us) rather than torch.cuda.current_stream() (3-4 us: a third of the host time per outer
-        iteration in the launch-latency regime)."""
+        """torch's current stream on this device as a cudaStream_t (a plain int: every prototype declares c_void_p).
+        Asked for at every launch, so it goes through the raw-handle query (0.2 us) rather than
+        torch.cuda.current_stream() (3-4 us: a third of the host time per outer iteration in the launch-latency regime)."""
         raw = self._raw_stream
         if raw is not None:
-            return C.c_void_p(raw(self.device_index))
-        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+            return raw(self.device_index)
+        return self.torch.cuda.current_stream().cuda_stream
 
     def zeros(self, n, dtype=None):
         return self.torch.zeros(int(n), dtype=dtype or self.torch.float64, device=self.device)
@@ -117,36 +121,35 @@ class Runtime:
 
     def mark(self, name, nbytes):
         """``with rt.mark("spmm", bytes): launch`` -- a no-op unless profiling is on"""
+        if self.prof is None:
+            return _NO_MARK
         return _Mark(self, name, nbytes)
 
     def pinned(self, n, dtype=None):
         return self.torch.empty(int(n), dtype=dtype or self.torch.float64, pin_memory=True)
 
     def read(self, t, count=None):
-        """small device tensor -> numpy (one async copy into pinned memory + stream sync)."""
+        """small device tensor -> numpy: gnk_scalars_fetch + gnk_scalars_wait (one async copy into pinned memory behind
+        everything enqueued on the current stream so far, then a wait for that copy)."""
         n = t.numel() if count is None else count
-        self._pinned[:n].copy_(t[:n], non_blocking=True)
-        self.sync()
+        lib, ctx = self.lib, self.ctx
+        if lib.gnk_scalars_fetch(ctx, t.data_ptr(), n, self._pinned_ptr, self.stream) or lib.gnk_scalars_wait(ctx):
+            _lib.check(-1, "scalar read-back")
         return self._pinned_np[:n].copy()
 
-    def mark_event(self):
-        """record an event on the current stream (one reusable event: the solvers keep at most one read in flight)"""
-        if getattr(self, "_event", None) is None:
-            self._event = self.torch.cuda.Event()
-            self._side = self.torch.cuda.Stream(device=self.device)
-        self._event.record()
-        return self._event
+    def read_begin(self, t, count):
+        """enqueue the read-back of ``t[:count]`` behind the work queued so far; ``read_end`` returns the values.
+        Kernels enqueued between the two calls keep the device busy while the host waits for the scalars
+        (gauss_newton_krylow's speculative basis expansion).  At most one such read is in flight (its own pinned
+        block, so a plain ``read`` in between does not disturb it)."""
+        if self.lib.gnk_scalars_fetch(self.ctx, t.data_ptr(), count, self._pinned2_ptr, self.stream):
+            _lib.check(-1, "gnk_scalars_fetch")
+        return count
 
-    def read_at(self, t, count, event):
-        """``read`` that waits only for the work enqueued BEFORE ``event`` (mark_event): the copy runs on a side stream,
-        so kernels enqueued on the main stream after the event keep the device busy while the host waits for the
-        scalars (gauss_newton_krylow's speculative basis expansion)."""
-        side = self._side
-        side.wait_event(event)
-        with self.torch.cuda.stream(side):
-            self._pinned[:count].copy_(t[:count], non_blocking=True)
-        side.synchronize()
-        return self._pinned_np[:count].copy()
+    def read_end(self, count):
+        if self.lib.gnk_scalars_wait(self.ctx):
+            _lib.check(-1, "gnk_scalars_wait")
+        return self._pinned2_np[:count].copy()
 
     def read_i32(self, t):
         self._pinned_i[:t.numel()].copy_(t, non_blocking=True)
@@ -198,6 +201,20 @@ class _Mark:
             e1.record()
             self.rt.prof.setdefault(self.name, []).append((self.e0, e1, self.nbytes))
         return False
+
+
+class _NoMark:
+    """what ``rt.mark`` hands out while no profile is being taken: one shared object, nothing recorded"""
+    __slots__ = ("cancel",)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_MARK = _NoMark()
 
 
 class SharedBuffersUnavailable(RuntimeError):
@@ -305,10 +322,13 @@ class NodeSharedBuffers:
 
 
 def ptr(t, offset=0):
-    """device pointer of a torch tensor (+ element offset) as c_void_p; None -> NULL"""
+    """device pointer of a torch tensor (+ element offset) as a plain int, None -> NULL (every prototype in _lib.py
+    declares c_void_p, which takes both; building a c_void_p object per argument cost ~25 us per outer iteration)"""
     if t is None:
-        return C.c_void_p(0)
-    return C.c_void_p(t.data_ptr() + offset * t.element_size())
+        return None
+    if offset:
+        return t.data_ptr() + offset * t.element_size()
+    return t.data_ptr()
 
 
 def get_runtime() -> Runtime:

@@ -392,11 +392,11 @@ def gauss_newton_krylow(
                 with rt.mark("residual", 32.0 * n_res_own):
                     prob.residual(x_trial, F_trial, loss_slot, aux=aux[1])
                 if spec_ok and state["spec"] is None:
-                    ev = rt.mark_event()       # the scalars of this trial are complete here ...
+                    pending_read = rt.read_begin(blk, _BLK)   # the scalars of this trial are complete here ...
                     jac_new = prob.jacobian(x_trial, aux=aux[1])
                     krylow.dev_expand_enqueue(*expansion_operands(jac_new), hx, ptr(blk, other_slot()))
                     state["spec"] = jac_new
-                    state["vals"] = rt.read_at(blk, _BLK, ev)   # ... and are read while the expansion runs
+                    state["vals"] = rt.read_end(pending_read)   # ... and are read while the expansion runs
                 else:
                     if state["spec"] is not None:
                         state["spec"] = False  # a later trial: the speculation belonged to a rejected one

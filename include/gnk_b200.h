@@ -68,6 +68,13 @@ int gnk_destroy(gnk_ctx* ctx);
 int gnk_sm_count(gnk_ctx* ctx);
 /* number of kernels this library has launched on this context since creation (bench: gpu_launches) */
 int64_t gnk_launch_count(gnk_ctx* ctx);
+/* The one host read-back of an outer iteration: the scalar block [d | ||JVd||^2 | ... | loss | flags] that
+ * gauss_newton_krylow.py:88-100 consumes on the host (armijo_goldstein.py:47-72 judges the trial with it).
+ * gnk_scalars_fetch enqueues the copy of `count` doubles to h_dst (page-locked host memory) behind the work queued on
+ * `stream` so far, on the context's own copy stream; gnk_scalars_wait blocks until the last fetch has landed.  Kernels
+ * enqueued on `stream` between the two calls overlap the host's wait (the speculative basis expansion, krylow.py:55-73). */
+int gnk_scalars_fetch(gnk_ctx* ctx, const double* d_src, int count, double* h_dst, void* stream);
+int gnk_scalars_wait(gnk_ctx* ctx);
 
 /* ---- Bratu residual / Jacobian (bratu_pde_problem.py:76-96) ----------------------------------- */
 /* F = y - (L u + alpha D u + lam e^u) on owned rows and `depth` (0|1) halo rows each side,

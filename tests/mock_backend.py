@@ -55,6 +55,13 @@ class MockLib:
     def gnk_sm_count(self, ctx):
         return 148
 
+    def gnk_scalars_fetch(self, ctx, d_src, count, h_dst, stream):
+        arr(h_dst, count)[:] = arr(d_src, count)   # the mock has no streams: the copy is immediate
+        return 0
+
+    def gnk_scalars_wait(self, ctx):
+        return 0
+
     # ---- bratu ----
     def _grid(self, lay, col, lo, hi):
         """rows [lo, hi) of a stored column as a 2-D view (row index relative to the first owned row)"""
@@ -449,11 +456,15 @@ class MockRuntime(device.Runtime):
             self.lib.rank, self.lib.world = self.rank, self.world
         self._pinned = torch.empty(4096, dtype=torch.float64)
         self._pinned_np = self._pinned.numpy()
+        self._pinned_ptr = self._pinned.data_ptr()
+        self._pinned2 = torch.empty(1024, dtype=torch.float64)
+        self._pinned2_np = self._pinned2.numpy()
+        self._pinned2_ptr = self._pinned2.data_ptr()
         self._pinned_i = torch.empty(16, dtype=torch.int32)
 
     @property
     def stream(self):
-        return C.c_void_p(0)
+        return 0
 
     def sync(self):
         pass
@@ -466,12 +477,6 @@ class MockRuntime(device.Runtime):
 
     def host_register(self, addr, nbytes):
         pass
-
-    def mark_event(self):
-        return None
-
-    def read_at(self, t, count, event):
-        return self.read(t, count)
 
     def launches(self):
         return self.lib.launches
