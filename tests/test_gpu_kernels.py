@@ -357,6 +357,50 @@ def test_cholqr2_norm_preservation_at_benchmark_size(g):
     assert np.allclose(v[k + 4:], np.abs(vh[k + 4:]), rtol=1e-12)
 
 
+@pytest.mark.parametrize("n,k", [(16384, 32), (20000, 33), (40002, 39), (65536, 40), (30000, 41), (50000, 47),
+                                 (16386, 48), (100000, 50), (262144, 55)])
+def test_wide_gram_qr_matches_householder_and_lstsq(g, n, k):
+    """33..56 panel columns (krylow_restart up to 55) on the tensor-pipe path: wide Gram kernel + dense Cholesky +
+    refinement pass (csrc/gram_cgls.cu: gnk_cholqr_wide_try), every block count (5..7 blocks of 8 columns), both
+    register-tile widths of the refinement kernel, partial last steps; same bars as the narrow path."""
+    rs = np.random.RandomState(n + 31 * k)
+    A = rs.normal(size=(n, k)) @ (np.eye(k) + 0.3 * rs.normal(size=(k, k)))
+    A *= np.exp(rs.uniform(-4, 4, size=k))[None, :]          # graded columns: CholeskyQR is scaling invariant
+    y = rs.normal(size=n)
+    cond = np.linalg.cond(A / np.linalg.norm(A, axis=0))
+    for sign in (1.0, -1.0):
+        vh = _raw_ls(g, A, y, sign, method=1)
+        xr = np.linalg.lstsq(sign * A, y, rcond=None)[0]
+        vc = _raw_ls(g, A, y, sign, method=0)
+        assert vc[k + 2] == 0 and vh[k + 2] == 0
+        assert rel(vc[:k], xr) < 1e-13 * max(cond, 10.0), (rel(vc[:k], xr), cond)
+        assert rel(vc[:k], vh[:k]) < 1e-13 * max(cond, 10.0)
+        for i, tol in ((k, 1e-9), (k + 1, 1e-11), (k + 3, 1e-11)):
+            assert abs(vc[i] - vh[i]) <= tol * abs(vh[i]), (i, vc[i], vh[i])
+        assert np.allclose(vc[k + 4:], np.abs(vh[k + 4:]), rtol=1e-9)
+        assert not np.array_equal(vc[:k], vh[:k]) or k == 0   # the two calls really took different paths
+    assert np.array_equal(_raw_ls(g, A, y, 1.0), _raw_ls(g, A, y, 1.0))
+    assert np.array_equal(_raw_ls(g, A * 2.0 ** 30, y * 2.0 ** 30, 1.0)[:k], _raw_ls(g, A, y, 1.0)[:k])
+
+
+def test_wide_gram_qr_refuses_and_falls_back(g):
+    """consistent system / nearly dependent columns / all-zero panel at 40 columns: sentinel, then Householder"""
+    rs = np.random.RandomState(13)
+    n, k = 20000, 40
+    A = rs.normal(size=(n, k))
+    x0 = rs.normal(size=k)
+    v = _raw_ls(g, A, A @ x0, 1.0)
+    assert v[k + 2] == -1 and np.all(v[:k] == 0) and v[k] == 0 and v[k + 3] == 0
+    assert rel(g.linear_least_squares(A, A @ x0), x0) < 1e-12
+    A2 = A.copy()
+    A2[:, 37] = A2[:, 2] + 1e-9 * rs.normal(size=n)
+    y = rs.normal(size=n)
+    assert _raw_ls(g, A2, y, 1.0)[k + 2] == -1
+    xh = _raw_ls(g, A2, y, 1.0, householder=True)
+    assert xh[k + 2] == 0 and rel(g.linear_least_squares(A2, y), xh[:k]) == 0.0
+    assert _raw_ls(g, np.zeros((16384, 35)), np.zeros(16384), 1.0)[35 + 2] == -1
+
+
 def test_tsqr_scalar_block_and_rank_deficiency(g, capsys):
     _lib, device = _lib_mods()
     from gauss_newton_via_generalized_krylov_subspaces_b200.gauss_newton_krylow import tsqr_solve

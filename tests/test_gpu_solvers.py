@@ -422,6 +422,34 @@ def test_gnk_with_cgls_inner_solve(g):
     assert abs(err(loose.x) - err(qr.x)) < 1e-3 * err(qr.x)
 
 
+def test_gnk_restart50_qr_on_the_wide_gram_path(g):
+    """krylow_restart=50 with the QR least squares on a 256 x 256 interior grid (65536 unknowns): panels of 33..51 columns
+    take the wide tensor-pipe path (gnk_cholqr_wide_try) instead of the Householder TSQR.  Checked against the oracle
+    (LAPACK QR) on the same inputs: counts equal, the first cycle within the 1e-10 bar wherever the panel is wide
+    (iterations 33..50; the early iterations of this grid carry the cancellation of DESIGN.md section 5), the end
+    point after the restart within the post-restart bar."""
+    o = orc.BratuOracle(257, 5, 10)
+    y, u0 = o.operator(o.u_true), o.start_vector(seed=42)
+    pb = g.BratuPdeProblem(257, 5, 10)
+    res, jac = pb.make_res(y), pb.make_jac()
+    idx = np.random.RandomState(0).choice(o.n, 64, replace=False)
+    ref_trace, our_trace = [], []
+    ref = orc.gnk(o.make_res(y), u0, o.make_jac(), restart=50, max_iter=61,
+                  callback=lambda x, **kw: ref_trace.append(np.asarray(x)[idx].copy()))
+    rt = g.get_runtime()
+    before = rt.launches()
+    out = g.gauss_newton_krylow(res, u0, jac, krylow_restart=50, max_iter=61,
+                                callback=lambda x, **kw: our_trace.append(np.asarray(x)[idx].copy()))
+    assert rt.launches() > before
+    assert (out.nit, out.nrev, out.njev, bool(out.success)) == (ref["nit"], ref["nfev"], ref["njev"], bool(ref["success"]))
+    assert len(our_trace) == len(ref_trace)
+    dev = [float(np.max(np.abs(a - b)) / np.max(np.abs(b))) for a, b in zip(our_trace, ref_trace)]
+    print("restart-50 QR, deviation per iteration:", " ".join(f"{d:.1e}" for d in dev))
+    assert max(dev[32:50]) < TOL, dev[32:50]
+    assert max(dev[:50]) < 1e-8 and max(dev) < 1e-5
+    assert rel(out.x, ref["x"]) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------------
 # SURVEY 8f(1): the experiment harness on live device vectors, and the reference's own driver script on this package
 # ------------------------------------------------------------------------------------------------
