@@ -10,6 +10,8 @@ A "step" is one complete GNK solve of a named workload (`--workload`, default = 
   bratu_1024_restart30   BASELINE config 3: grid_nodes=1025, krylow_restart=30, max_iter=100 -> 99 iterations
   bratu_8192_k50_cgls    BASELINE config 5: grid_nodes=8193 (67M unknowns), krylow_restart=50, projected least squares
                          by CGLS (cg_rtol 1e-4), max_iter=101 -> 100 iterations; meant for 8 GPUs
+  bratu_8192_k50_qr      the same run with the reference's own projected least squares (QR): panels of 33..51 columns
+                         take the wide tensor-pipe path (gnk_cholqr_wide_try)
 
   value     iterations/s with u0 and y resident in HBM and the result left in HBM
   e2e       the same through the public API with HOST buffers: make_res(y) + gauss_newton_krylow(res, u0, jac) -> host
@@ -53,6 +55,7 @@ WORKLOADS = {
     "bratu_1024_restart30": dict(grid_nodes=1025, restart=30, iters=99, ls="qr", cg_rtol=None,
                                  golden=("bratu_g1025", "gnk_restart30", "bratu_g1025_sens")),
     "bratu_8192_k50_cgls": dict(grid_nodes=8193, restart=50, iters=100, ls="cgls", cg_rtol=1e-4, golden=None),
+    "bratu_8192_k50_qr": dict(grid_nodes=8193, restart=50, iters=100, ls="qr", cg_rtol=None, golden=None),
 }
 
 
@@ -519,16 +522,17 @@ def run_ours(a):
                 want.append("bratu_1024_restart30")
             if world == 8:
                 want.append("bratu_8192_k50_cgls")
+                want.append("bratu_8192_k50_qr")
     elif a.extras == "none":
         want = []
     else:
         want = [w for w in a.extras.split(",") if w]
     for w in want:
-        st, wu = (5, 3) if w != "bratu_8192_k50_cgls" else (3, 3)
+        st, wu = (5, 3) if not w.startswith("bratu_8192") else (3, 3)
         e = h.measure(w, st, wu, e2e=not a.no_e2e, parity=not a.no_parity)
         e["config"] = workload_config(a, workload_spec(a, w), w, world)
         e["metric"], e["unit"] = METRIC, UNIT
-        if w == "bratu_8192_k50_cgls":
+        if w.startswith("bratu_8192"):
             e["cpu_reference"] = ("not runnable: the reference's CPU path at 8192^2 / 50 columns exceeds host RAM (SURVEY "
                                   "8d: 24 GB at 4096^2 / 30 columns); extrapolated linearly in n and k from the measured "
                                   "4096^2 run it would be ~0.01 it/s")

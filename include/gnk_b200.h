@@ -146,7 +146,10 @@ int gnk_cgs_update(gnk_ctx* ctx, const gnk_layout* lay, const double* d_V, int k
  * the least-squares solution with an error of second order in the remaining gradient, and d_out[k+1] = ||y - A d0||^2
  * of the normal-equation solution d0).  That path REFUSES panels whose Gram matrix is numerically rank
  * deficient (pivot ratio < 1e-12, e.g. a consistent system) or whose refinement step is not small: it then writes
- * d = 0 and d_out[k+2] = -1, and the caller re-issues the call after gnk_tsqr_ls_method(ctx, 1). */
+ * d = 0 and d_out[k+2] = -1, and the caller re-issues the call after gnk_tsqr_ls_method(ctx, 1).
+ * Panels of 33 <= k+1 <= 56 columns under the same conditions (krylow_restart up to 55; method 0 only) take the same
+ * scheme with a wider Gram sweep (5..7 column blocks), a dense Cholesky in one CTA and the refinement form
+ * (gram_cgls.cu: gnk_cholqr_wide_try), with the same result block and the same refusal convention. */
 int gnk_tsqr_ls(gnk_ctx* ctx, const double* d_A, int64_t lda, int64_t n_rows, int k,
                 const double* d_y, double sign_a, double* d_out, void* stream);
 

@@ -80,6 +80,27 @@ def main():
         d = np.max(np.abs(xs - gr["xs"]) / np.max(np.abs(gr["xs"]), axis=1, keepdims=True), axis=1)
         print(f"[multi] G=1025 world={world}: nit={out.nit} max dev {d.max():.2e} tail dev {d[4:].max():.2e} ok", flush=True)
 
+    # ---- krylow_restart=50 with the QR least squares at 256^2: panels of 33..51 columns take the wide tensor-pipe path
+    # (gnk_cholqr_wide_try: the Gram matrices and the refinement vectors are summed over the ranks inside the single-CTA
+    # factor kernels) wherever every rank's slab has >= 16384 unknowns (world <= 4), the Householder TSQR otherwise.
+    # Checked against the oracle (LAPACK QR) on the same inputs.
+    o = orc.BratuOracle(257, 5, 10)
+    y, u0 = o.operator(o.u_true), o.start_vector(seed=42)
+    pb = g.BratuPdeProblem(257, 5, 10)
+    res, jac = pb.make_res(y), pb.make_jac()
+    idx = np.random.RandomState(0).choice(o.n, 64, replace=False)
+    ref_trace, our_trace = [], []
+    ref = orc.gnk(o.make_res(y), u0, o.make_jac(), restart=50, max_iter=61,
+                  callback=lambda x, **kw: ref_trace.append(np.asarray(x)[idx].copy()))
+    out = g.gauss_newton_krylow(res, u0, jac, krylow_restart=50, max_iter=61,
+                                callback=lambda x, **kw: our_trace.append(np.asarray(x)[idx].copy()))
+    assert (out.nit, out.nrev, out.njev) == (ref["nit"], ref["nfev"], ref["njev"]) and gather_equal(out.x)
+    dev = [float(np.max(np.abs(a - b)) / np.max(np.abs(b))) for a, b in zip(our_trace, ref_trace)]
+    assert len(dev) == 60 and max(dev[1:50]) < 1e-10 and max(dev) < 1e-5, dev
+    if rank == 0:
+        print(f"[multi] G=257 restart 50 (QR) world={world}: nit={out.nit} max dev first cycle {max(dev[:50]):.2e} "
+              f"(wide panels {max(dev[32:50]):.2e}) after the restart {max(dev[50:]):.2e} ok", flush=True)
+
     # ---- the north-star workload itself: Bratu 4096^2, k = 1..30, golden trace of the reference --------------------
     # (skipped with GNK_MULTI_SKIP_4096=1 for quick plumbing checks)
     if os.environ.get("GNK_MULTI_SKIP_4096", "0") != "1":
