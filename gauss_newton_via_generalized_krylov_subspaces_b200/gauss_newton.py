@@ -152,6 +152,14 @@ def gauss_newton(
             for j in range(p):
                 rt.upload(np.ascontiguousarray(dense[:, j]), dA[j * lda:j * lda + n_res])
             tsqr_solve(rt, dA, lda, n_res, p, F[res_off:], -1.0, blk, householder=True)
+            # scipy.linalg.lstsq (:126) is SVD-based and returns the minimum-norm step for a rank-deficient J; the QR here
+            # has no such branch, and an exactly singular R would hand inf/NaN to 100 Armijo trials.  Say so instead.
+            ls_vals = rt.read(blk, 2 * p + 4)
+            if np.any(ls_vals[p + 4:2 * p + 4] == 0.0) or not np.all(np.isfinite(ls_vals[:p])):
+                raise np.linalg.LinAlgError(
+                    "gauss_newton: the dense Jacobian is rank deficient (a zero on the diagonal of its R factor); the "
+                    "reference's scipy.linalg.lstsq would return the minimum-norm step here, which the device QR does "
+                    "not implement")
             d[off:off + p].copy_(blk[:p])
 
         if native_armijo:

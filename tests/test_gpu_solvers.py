@@ -309,6 +309,15 @@ def test_rosenbrock_3d_dense_jacobian(g):
     assert np.allclose(out.x, [1.0, 1.0], atol=1e-12)
 
 
+def test_gauss_newton_dense_rank_deficient_jacobian_is_reported(g):
+    """a dense Jacobian with a zero column: the reference's scipy.linalg.lstsq returns the minimum-norm step; the device
+    QR has no such branch and says so instead of handing inf/NaN to 100 Armijo trials (advisor, round 1)"""
+    res = lambda x: np.array([x[0] - 1.0, 2.0 * x[0] + 1.0, x[0]])
+    jac = lambda x: np.array([[1.0, 0.0], [2.0, 0.0], [1.0, 0.0]])
+    with pytest.raises(np.linalg.LinAlgError, match="rank deficient"):
+        g.gauss_newton(res, np.array([1.0, 2.0]), jac, callback=lambda **k: None)
+
+
 def test_powell_step_length_plugins(g):
     """powell_divergence_test.py: args=(tau,), max_iter=19, three step-length controls incl. user plug-ins."""
     def pres(x, tau):

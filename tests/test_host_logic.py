@@ -249,6 +249,14 @@ def test_host_gn_and_foreign_callables(g):
     assert (out.nit, out.nrev, out.njev) == (5, 6, 5) and list(rec.cg) == list(gr["cg_iter"])
 
 
+def test_host_gn_dense_rank_deficient_jacobian_is_reported(g):
+    """advisor: a dense Jacobian with a zero column must not hand inf/NaN to the line search"""
+    res = lambda x: np.array([x[0] - 1.0, 2.0 * x[0] + 1.0, x[0]])
+    jac = lambda x: np.array([[1.0, 0.0], [2.0, 0.0], [1.0, 0.0]])
+    with pytest.raises(np.linalg.LinAlgError, match="rank deficient"):
+        g.gauss_newton(res, np.array([1.0, 2.0]), jac, callback=lambda **k: None)
+
+
 def test_host_step_length_plugins_and_errors(g):
     def pres(x, tau):
         return np.array([x[0] + 1, tau * x[0] ** 2 + x[0] - 1])
