@@ -1,7 +1,7 @@
 """Device time of gnk_tsqr_ls on panels of 33..56 columns: the wide tensor-pipe path (gram_cgls.cu: gnk_cholqr_wide_try)
 against the Householder TSQR it replaces there.  Development aid.
 
-    python tools/bench_wide_ls.py [n_rows]        (default 8388608 = one rank's slab of BASELINE config 5)
+    python tools/bench_wide_ls.py [n_rows] [k,k,...]     (default 8388608 rows = one rank's slab of BASELINE config 5)
 """
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,7 +13,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 8388608
 rt = g.get_runtime()
 out = rt.zeros(2 * 256 + 8)
 res = {"n_rows": n, "ms": {}}
-for k in (31, 33, 40, 47, 50, 55):
+ks = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [31, 33, 40, 47, 50, 55]
+for k in ks:
     A = torch.randn(k * n, dtype=torch.float64, device=rt.device)
     y = torch.randn(n, dtype=torch.float64, device=rt.device)
     row = {}
