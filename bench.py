@@ -529,7 +529,11 @@ def run_ours(a):
         want = [w for w in a.extras.split(",") if w]
     for w in want:
         st, wu = (5, 3) if not w.startswith("bratu_8192") else (3, 3)
-        e = h.measure(w, st, wu, e2e=not a.no_e2e, parity=not a.no_parity)
+        try:
+            e = h.measure(w, st, wu, e2e=not a.no_e2e, parity=not a.no_parity)
+        except Exception as exc:  # an extra workload must never cost the headline line (raised alike on every rank)
+            extras[w] = dict(error=f"{type(exc).__name__}: {exc}")
+            continue
         e["config"] = workload_config(a, workload_spec(a, w), w, world)
         e["metric"], e["unit"] = METRIC, UNIT
         if w.startswith("bratu_8192"):
