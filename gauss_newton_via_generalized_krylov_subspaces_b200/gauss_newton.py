@@ -91,13 +91,23 @@ def gauss_newton(
     x0_host = np.asarray(x0, dtype=np.float64).reshape(-1)
     prob = resolve_problem(res, jac, x0_host, args)
     is_bratu = isinstance(prob, BratuDeviceProblem)
-    if is_bratu and prob.distributed:
-        raise NotImplementedError("gauss_newton: the full-space solver runs on one GPU (replicas only)")
     require_single_rank_unless_sharded(rt, prob, "gauss_newton")
+    # Several ranks (Bratu only: row slabs, as in gauss_newton_krylow): the CG solve exchanges one halo row per operator
+    # application and all-reduces its dot products inside gnk_cgls; out here the step d gets its two halo rows from the
+    # neighbours once per iteration, so that J d and the trial points x + s d -- formed on the WHOLE stored column -- are
+    # valid on the halo rows without further exchanges, and the k-independent scalars are summed over the ranks.
+    dist = is_bratu and prob.distributed
     success = False
     cg_iter = None
     sol = prob.sol_fields
     p, off, ld = sol["n_own"], sol["off"], sol["ld"]
+
+    # entries of a solution vector that x + s d runs over: the owned part, or the stored rows incl. halos when sharded
+    ax_n, ax_off = (p + 2 * off, 0) if dist else (p, off)
+
+    def reduce(slot, count, op=0):
+        if dist:
+            rt.allreduce(scal[slot:slot + count], count, op)
 
     x = prob.new_sol()
     prob.upload_x(x0_host, x)
@@ -162,17 +172,22 @@ def gauss_newton(
                     "not implement")
             d[off:off + p].copy_(blk[:p])
 
+        if dist:
+            prob.d.halo_exchange(d, 2)
+
         if native_armijo:
             # g = sum((J d)^2), then trials x + s d  (armijo_goldstein.py:49-62)
             jac_ev.matmat(d, ld, 1, Jd, ldr) if not is_bratu else prob.d.apply(
                 jac_ev.expu, d, ld, 1, -jac_ev.scale, 0, Jd, ldr, res_off)
             prob.sumsq(Jd, scal[2:4], res_lay) if not is_bratu else _lib.check(
                 lib.gnk_norm_stats(rt.ctx, C.byref(res_lay), ptr(Jd), ptr(scal, 2), rt.stream), "gnk_norm_stats")
+            reduce(2, 2, 2)
             _lib.check(lib.gnk_dot(rt.ctx, p, ptr(d, off), ptr(d, off), ptr(scal, 5), rt.stream), "gnk_dot")
+            reduce(5, 1)
 
             def trial_loss(s):
-                _lib.check(lib.gnk_axpby(rt.ctx, p, 1.0, ptr(x, off), float(s), ptr(d, off), ptr(x_trial, off),
-                                         rt.stream), "gnk_axpby")
+                _lib.check(lib.gnk_axpby(rt.ctx, ax_n, 1.0, ptr(x, ax_off), float(s), ptr(d, ax_off),
+                                         ptr(x_trial, ax_off), rt.stream), "gnk_axpby")
                 if is_bratu:
                     prob.residual(x_trial, F_trial, scal, aux=aux_trial)
                 else:
@@ -197,9 +212,11 @@ def gauss_newton(
             r_host = np.asarray(r_new, dtype=np.float64).reshape(-1)
             prob.upload_x(r_host, F_trial) if is_bratu else rt.upload(r_host, F_trial[:n_res])
             _lib.check(lib.gnk_norm_stats(rt.ctx, C.byref(res_lay), ptr(F_trial), ptr(scal), rt.stream), "gnk_norm_stats")
+            reduce(0, 2, 2)
             _lib.check(lib.gnk_dot(rt.ctx, p, ptr(d, off), ptr(d, off), ptr(scal, 5), rt.stream), "gnk_dot")
-            _lib.check(lib.gnk_axpby(rt.ctx, p, 1.0, ptr(x, off), float(step_length), ptr(d, off), ptr(x_trial, off),
-                                     rt.stream), "gnk_axpby")
+            reduce(5, 1)
+            _lib.check(lib.gnk_axpby(rt.ctx, ax_n, 1.0, ptr(x, ax_off), float(step_length), ptr(d, ax_off),
+                                     ptr(x_trial, ax_off), rt.stream), "gnk_axpby")
             v = rt.read(scal, 8)
             squared_sum_d = float(v[5])
             new_loss = float(v[0])
@@ -208,6 +225,7 @@ def gauss_newton(
         nfev += nfev_delta
 
         _lib.check(lib.gnk_dot(rt.ctx, p, ptr(x, off), ptr(x, off), ptr(scal, 4), rt.stream), "gnk_dot")
+        reduce(4, 1)
         squared_sum_x_prev = float(rt.read(scal, 8)[4])
 
         # x += s d  (the accepted trial point is exactly that)

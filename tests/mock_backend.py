@@ -337,6 +337,8 @@ class MockLib:
             def apply(v, tr):
                 vin = np.zeros(ld)
                 vin[off:off + n] = v
+                if self.world > 1:  # cgls.cu: Cg::apply exchanges one halo row of the input first
+                    self.gnk_comm_halo_exchange(None, lay, C.c_void_p(vin.ctypes.data), 1, None)
                 vout = np.zeros(ld)
                 self.gnk_stencil_apply(None, lay, prm, C.c_void_p(op.d_expu or 0), C.c_void_p(vin.ctypes.data), ld, 1,
                                        op.sign, tr, C.c_void_p(vout.ctypes.data), ld, off, None)
@@ -357,6 +359,8 @@ class MockLib:
             minv = 1.0 / np.asarray(A.multiply(A).sum(axis=0)).reshape(-1)
             xv = arr(x, op.p)
         from oracle.gnk_oracle import pcg
+        if self.world > 1:
+            pcg = self._pcg_sharded
         b = apply(yv, 1)
         mv = lambda v: apply(apply(v, 0), 1)  # noqa: E731
         total = 0
@@ -368,6 +372,36 @@ class MockLib:
         xv[:] = sol
         it_out.value = total + its
         return 0
+
+    def _pcg_sharded(self, matvec, b, minv=None, rtol=1e-5, maxiter=None, x0=None):
+        """oracle.gnk_oracle.pcg on row-sharded vectors: every inner product is summed over the ranks in rank order
+        (cgls.cu: Cg::reduce), maxiter counts the GLOBAL unknowns"""
+        dot = lambda u, v: float(self._allgather(np.array([np.dot(u, v)])).sum())  # noqa: E731
+        bn = np.sqrt(dot(b, b))
+        atol = max(0.0, rtol * bn)
+        if bn == 0:
+            return b, 0
+        if maxiter is None:
+            maxiter = 10 * int(self._allgather(np.array([float(b.shape[0])])).sum())
+        if x0 is None:
+            x, r = np.zeros_like(b), b.copy()
+        else:
+            x = np.array(x0, dtype=np.float64)
+            r = b - matvec(x)
+        rho_prev, p, its = None, None, 0
+        for it in range(maxiter):
+            if np.sqrt(dot(r, r)) < atol:
+                break
+            z = r if minv is None else minv * r
+            rho = dot(r, z)
+            p = z.copy() if it == 0 else p * (rho / rho_prev) + z
+            q = matvec(p)
+            a = rho / dot(p, q)
+            x += a * p
+            r -= a * q
+            rho_prev = rho
+            its += 1
+        return x, its
 
     # ---- comm over torch.distributed (gloo) ----
     def _allgather(self, v):

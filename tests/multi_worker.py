@@ -80,6 +80,28 @@ def main():
         d = np.max(np.abs(xs - gr["xs"]) / np.max(np.abs(gr["xs"]), axis=1, keepdims=True), axis=1)
         print(f"[multi] G=1025 world={world}: nit={out.nit} max dev {d.max():.2e} tail dev {d[4:].max():.2e} ok", flush=True)
 
+    # ---- gauss_newton (full space, CGLS inner solve) and cg_least_squares on row slabs: golden traces of the reference
+    # at grid_nodes=101 (m = 100: uneven slabs at 3+ ranks do not occur here, 100 = 2*50 = 4*25 = 8*12.5 -> 13/12 rows)
+    gd = Golden("bratu_g101")
+    pb = g.BratuPdeProblem(101, 5, 10)
+    res, jac, err = pb.make_res(gd["y"]), pb.make_jac(), pb.make_error()
+    for precond in (False, True):
+        gr = gd.run("gn_precond" if precond else "gn")
+        rec = Recorder(gr["sample_idx"], err)
+        out = g.gauss_newton(res, gd["u0"], jac, callback=rec, cg_preconditioner=precond)
+        assert (out.nit, out.nrev, out.njev, out.success) == (4, 5, 4, True), (out.nit, out.nrev, out.njev, out.success)
+        assert rec.err[-1] < 1e-10 and rel(out.x, gr["x_final"]) < 1e-10 and gather_equal(out.x)
+        for a, b in zip(rec.cg, gr["cg_iter"]):  # CG counts are rounding-sensitive: +-2 %
+            assert abs(a - b) <= max(2, 0.02 * b), (rec.cg, list(gr["cg_iter"]))
+    o = orc.BratuOracle(101, 5, 10)
+    r0 = o.make_res(gd["y"])(gd["u0"])
+    xo, ito = orc.cgls(-1 * o.make_jac()(gd["u0"]), r0, rtol=1e-6)
+    xc, itc = g.cg_least_squares(-1 * jac(gd["u0"]), r0, cg_rtol=1e-6)
+    assert rel(xc, xo) < 1e-6 and abs(itc - ito) <= max(2, 0.02 * ito) and gather_equal(xc)
+    if rank == 0:
+        print(f"[multi] G=101 gauss_newton world={world}: nit=4, cg iterations {list(rec.cg)} (reference "
+              f"{list(gr['cg_iter'])}); cg_least_squares {itc} iterations (oracle {ito}) ok", flush=True)
+
     # ---- krylow_restart=50 with the QR least squares at 256^2: panels of 33..51 columns take the wide tensor-pipe path
     # (gnk_cholqr_wide_try: the Gram matrices and the refinement vectors are summed over the ranks inside the single-CTA
     # factor kernels) wherever every rank's slab has >= 16384 unknowns (world <= 4), the Householder TSQR otherwise.

@@ -82,6 +82,83 @@ def test_sharded_gnk_matches_reference_golden(world, tmp_path):
         assert np.array_equal(z["x"], outs[0]["x"]) and np.array_equal(z["xnorm"], outs[0]["xnorm"])
 
 
+def _gn_worker(rank, world, port, G, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mock_backend
+    mock_backend.install()
+    import gauss_newton_via_generalized_krylov_subspaces_b200 as g
+    from golden_util import Golden
+
+    gd = Golden(f"bratu_g{G}")
+    pb = g.BratuPdeProblem(G, 5, 10)
+    res, jac = pb.make_res(gd["y"]), pb.make_jac()
+    out = {}
+    for tag, precond in (("gn", False), ("gnp", True)):
+        xs, its, nf = [], [], []
+        o = g.gauss_newton(res, gd["u0"], jac, max_iter=9, cg_preconditioner=precond,
+                           callback=lambda x, nfev, cg_iter: (xs.append(np.asarray(x).copy()), its.append(cg_iter),
+                                                              nf.append(nfev)))
+        out.update({f"{tag}_xs": np.array(xs), f"{tag}_cg": np.array(its), f"{tag}_nfev": np.array(nf), f"{tag}_x": o.x,
+                    f"{tag}_counts": np.array([o.nit, o.nrev, o.njev, int(o.success)])})
+    # the user plug-in route of step_length_control (host objects, gauss_newton.py:118-120) on several ranks
+    calls = []
+
+    def plug(res_, x, r, J, args, d):
+        calls.append(1)
+        return g.armijo_goldstein(res_, x, r, J, args, d)
+    o = g.gauss_newton(res, gd["u0"], jac, max_iter=4, step_length_control=plug, callback=lambda **k: None)
+    out["plug_x"], out["plug_calls"] = o.x, np.array([len(calls)])
+    # cg_least_squares on the sharded stencil operator, with and without an initial guess
+    J = jac(gd["u0"])
+    r0 = res(gd["u0"])
+    x1, it1 = g.cg_least_squares(-1 * J, r0, cg_rtol=1e-6)
+    x2, it2 = g.cg_least_squares(-1 * J, r0, x0=0.5 * x1, cg_rtol=1e-6, preconditioner=False)
+    out.update(cg_x=x1, cg_it=np.array([it1, it2]), cg_x2=x2)
+    np.savez(os.path.join(out_dir, f"gn{rank}.npz"), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_gauss_newton_matches_the_single_rank_oracle(world, tmp_path):
+    """gauss_newton (gauss_newton.py:63-138) and cg_least_squares (:11-60) on row slabs: halo exchange per operator
+    application and rank-ordered dot products inside the CG solve, the step's halo rows once per outer iteration."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import Golden, rel
+    from oracle import gnk_oracle as orc
+    G = 34
+    mp.spawn(_gn_worker, args=(world, _free_port(), G, str(tmp_path)), nprocs=world, join=True)
+    gd = Golden(f"bratu_g{G}")
+    o = orc.BratuOracle(G, 5, 10)
+    outs = [np.load(os.path.join(tmp_path, f"gn{r}.npz")) for r in range(world)]
+    for tag, precond in (("gn", False), ("gnp", True)):
+        xs, its, nf = [], [], []
+        ref = orc.gn(o.make_res(gd["y"]), gd["u0"], o.make_jac(), max_iter=9, cg_preconditioner=precond,
+                     callback=lambda x, nfev, cg_iter: (xs.append(x.copy()), its.append(cg_iter), nf.append(nfev)))
+        for z in outs:
+            assert list(z[f"{tag}_counts"]) == [ref["nit"], ref["nfev"], ref["njev"], int(ref["success"])]
+            assert list(z[f"{tag}_nfev"]) == nf
+            # CG counts are rounding-sensitive (another summation order): a count or two per solve
+            assert np.all(np.abs(z[f"{tag}_cg"] - np.array(its)) <= np.maximum(2, 0.02 * np.array(its)))
+            assert rel(z[f"{tag}_xs"], np.array(xs)) < 1e-5      # cg_rtol = 1e-4 solves: the iterates agree to the CG tolerance
+            assert rel(z[f"{tag}_x"], ref["x"]) < 1e-5
+    J0 = o.make_jac()(gd["u0"])
+    r0 = o.make_res(gd["y"])(gd["u0"])
+    x1, it1 = orc.cgls(-1 * J0, r0, rtol=1e-6)
+    x2, it2 = orc.cgls(-1 * J0, r0, rtol=1e-6, preconditioner=False, x0=0.5 * x1)
+    for z in outs:
+        assert rel(z["cg_x"], x1) < 1e-6 and rel(z["cg_x2"], x2) < 1e-6
+        assert abs(int(z["cg_it"][0]) - it1) <= 2 and abs(int(z["cg_it"][1]) - it2) <= 3
+        assert int(z["plug_calls"][0]) == 3
+    for z in outs[1:]:                                           # every rank holds the same global results, bit for bit
+        for key in ("gn_x", "gnp_x", "plug_x", "cg_x", "cg_x2"):
+            assert np.array_equal(z[key], outs[0][key])
+
+
 def _replicated_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
