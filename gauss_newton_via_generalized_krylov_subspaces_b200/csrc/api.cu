@@ -65,6 +65,8 @@ int gnk_destroy(gnk_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->fetch_stream) cudaStreamDestroy(ctx->fetch_stream);
   if (ctx->fetch_event) cudaEventDestroy(ctx->fetch_event);
+  for (cudaEvent_t e : ctx->cg_event)
+    if (e) cudaEventDestroy(e);
   delete ctx;
   return 0;
 }
@@ -79,11 +81,7 @@ int64_t gnk_launch_count(gnk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 // a stream synchronisation through the framework (~25 us of host time per outer iteration in the latency regime).
 int gnk_scalars_fetch(gnk_ctx* ctx, const double* d_src, int count, double* h_dst, void* stream) {
   GNK_REQUIRE(ctx && d_src && h_dst && count >= 1, "gnk_scalars_fetch: bad argument");
-  if (!ctx->fetch_stream) {
-    GNK_CUDA(cudaSetDevice(ctx->device));
-    GNK_CUDA(cudaStreamCreateWithFlags(&ctx->fetch_stream, cudaStreamNonBlocking));
-    GNK_CUDA(cudaEventCreateWithFlags(&ctx->fetch_event, cudaEventDisableTiming));
-  }
+  if (int rc = gnk_ensure_fetch_stream(ctx)) return rc;
   GNK_CUDA(cudaEventRecord(ctx->fetch_event, (cudaStream_t)stream));
   GNK_CUDA(cudaStreamWaitEvent(ctx->fetch_stream, ctx->fetch_event, 0));
   GNK_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->fetch_stream));
@@ -97,3 +95,12 @@ int gnk_scalars_wait(gnk_ctx* ctx) {
 }
 
 }  // extern "C"
+
+int gnk_ensure_fetch_stream(gnk_ctx* ctx) {
+  if (!ctx->fetch_stream) {
+    GNK_CUDA(cudaSetDevice(ctx->device));
+    GNK_CUDA(cudaStreamCreateWithFlags(&ctx->fetch_stream, cudaStreamNonBlocking));
+    GNK_CUDA(cudaEventCreateWithFlags(&ctx->fetch_event, cudaEventDisableTiming));
+  }
+  return 0;
+}

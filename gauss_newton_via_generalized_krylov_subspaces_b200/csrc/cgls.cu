@@ -6,8 +6,12 @@
 // preconditioned one (:50-58); the reported iteration count is the sum.
 // A = sign*P for the Bratu stencil (matrix free; A p and A^T t are the same SpMV / SpMV-transpose kernels the
 // Krylov path uses) or a CSR pair for generic Jacobians.  All scalars (rho, p.q, alpha, beta) stay on the
-// device; the host reads one double (||r||^2) per iteration for the stopping test.
+// device; the host reads one double (||r||^2) per iteration for the stopping test -- one iteration LATE: iteration i + 1
+// is queued before the test of iteration i is looked at, and the two kernels that change the CG state (direction, step)
+// repeat the test on the device and do nothing once it has fired, so the device never waits for the host and the result
+// is the one scipy's loop produces.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -15,7 +19,8 @@ int gnk_comm_allgather_doubles(gnk_ctx* ctx, const double* d_send, double* d_rec
 
 namespace {
 constexpr int TPB = 256;
-enum { S_RR = 0, S_RHO = 1, S_RHO_PREV = 2, S_PQ = 3, S_BB = 4 };
+// (rr, rho) of iteration i live in slot pair S_RR + 8 (i & 1) .. so that the late read of iteration i cannot see i + 1's
+enum { S_RR = 0, S_RHO = 1, S_RHO_PREV = 2, S_PQ = 3, S_BB = 4, S_ALT = 8 };
 
 // z = minv * r (or r), rr = r.r, rho = r.z
 __global__ void __launch_bounds__(TPB) cg_precond_kernel(int64_t n, const double* __restrict__ r,
@@ -54,10 +59,13 @@ __global__ void __launch_bounds__(TPB) cg_precond_kernel(int64_t n, const double
 }
 
 // p = z + (rho/rho_prev) p   (first: p = z)
+// rrho = (rr, rho) of this iteration; a no-op once the stopping test sqrt(rr) < atol has fired (the host learns one
+// iteration later and stops queueing)
 __global__ void __launch_bounds__(TPB) cg_direction_kernel(int64_t n, const double* __restrict__ z,
                                                             double* __restrict__ p, const double* __restrict__ scal,
-                                                            int first) {
-  const double beta = first ? 0.0 : scal[S_RHO] / scal[S_RHO_PREV];
+                                                            const double* __restrict__ rrho, double atol, int first) {
+  if (sqrt(rrho[0]) < atol) return;
+  const double beta = first ? 0.0 : rrho[1] / scal[S_RHO_PREV];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     p[i] = first ? z[i] : fma(beta, p[i], z[i]);
@@ -66,8 +74,10 @@ __global__ void __launch_bounds__(TPB) cg_direction_kernel(int64_t n, const doub
 // x += alpha p, r -= alpha q, alpha = rho / p.q ; afterwards rho_prev <- rho
 __global__ void __launch_bounds__(TPB) cg_step_kernel(int64_t n, const double* __restrict__ p,
                                                        const double* __restrict__ q, double* __restrict__ x,
-                                                       double* __restrict__ r, double* __restrict__ scal) {
-  const double rho = scal[S_RHO];
+                                                       double* __restrict__ r, double* __restrict__ scal,
+                                                       const double* __restrict__ rrho, double atol) {
+  if (sqrt(rrho[0]) < atol) return;
+  const double rho = rrho[1];
   const double alpha = rho / scal[S_PQ];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -108,6 +118,23 @@ struct Cg {
   int reduce(double* d, int count) {
     if (ctx->nranks == 1) return 0;
     return gnk_comm_allreduce(ctx, d, count, 0, st);
+  }
+  // late read of the stopping test: copy rrho[0] on the context's copy stream behind the work queued so far (slot s of
+  // two); wait(s) blocks until that copy has landed
+  int fetch(const double* rrho, int s) {
+    if (int rc = gnk_ensure_fetch_stream(ctx)) return rc;
+    for (int e = 0; e < 4; ++e)
+      if (!ctx->cg_event[e]) GNK_CUDA(cudaEventCreateWithFlags(&ctx->cg_event[e], cudaEventDisableTiming));
+    GNK_CUDA(cudaEventRecord(ctx->cg_event[s], st));
+    GNK_CUDA(cudaStreamWaitEvent(ctx->fetch_stream, ctx->cg_event[s], 0));
+    GNK_CUDA(cudaMemcpyAsync(ctx->h_pinned + 8 + s, rrho, sizeof(double), cudaMemcpyDeviceToHost, ctx->fetch_stream));
+    GNK_CUDA(cudaEventRecord(ctx->cg_event[2 + s], ctx->fetch_stream));
+    return 0;
+  }
+  int wait(int s, double* host) {
+    GNK_CUDA(cudaEventSynchronize(ctx->cg_event[2 + s]));
+    *host = ctx->h_pinned[8 + s];
+    return 0;
   }
   int read(int slot, int count, double* host) {
     GNK_CUDA(cudaMemcpyAsync(ctx->h_pinned, scal + slot, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
@@ -198,24 +225,47 @@ extern "C" int gnk_cgls_x0(gnk_ctx* ctx, const gnk_linop* op, const double* d_y,
       GNK_CUDA(cudaMemsetAsync(d_x + o, 0, sizeof(double) * n, st));
       GNK_CUDA(cudaMemcpyAsync(r + o, b + o, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     }
-    for (int64_t it = 0; it < maxiter; ++it) {
+    static const bool pipelined = !(getenv("GNK_CG_PIPELINE") && atoi(getenv("GNK_CG_PIPELINE")) == 0);
+    int64_t done_at = -1;  // the first iteration whose stopping test fired
+    int64_t it = 0;
+    for (; it < maxiter; ++it) {
+      const int s = (int)(it & 1);
+      double* rrho = cg.scal + S_RR + S_ALT * s;
       cg_precond_kernel<<<cg.grid, TPB, 0, st>>>(n, r + o, use_m ? dinv + o : nullptr, z + o, part,
-                                                 ctx->d_tickets + TK_CG, cg.scal);
+                                                 ctx->d_tickets + TK_CG, rrho);
       GNK_LAUNCH_CHECK(ctx);
-      if (int rc = cg.reduce(cg.scal + S_RR, 2)) return rc;
-      double rr;
-      if (int rc = cg.read(S_RR, 1, &rr)) return rc;
-      if (sqrt(rr) < atol) break;
-      cg_direction_kernel<<<cg.grid, TPB, 0, st>>>(n, z + o, pv + o, cg.scal, it == 0 ? 1 : 0);
+      if (int rc = cg.reduce(rrho, 2)) return rc;
+      if (int rc = cg.fetch(rrho, s)) return rc;                 // ||r||^2 of iteration `it`, looked at one iteration later
+      if (!pipelined) {  // GNK_CG_PIPELINE=0: look at it now (the device idles while the host waits and re-queues)
+        double rr_now;
+        if (int rc = cg.wait(s, &rr_now)) return rc;
+        if (sqrt(rr_now) < atol) {
+          done_at = it;
+          break;
+        }
+      } else if (it > 0) {
+        double rr_prev;
+        if (int rc = cg.wait(1 - s, &rr_prev)) return rc;
+        if (sqrt(rr_prev) < atol) {  // iteration it - 1 had converged: its direction / step kernels did nothing
+          done_at = it - 1;
+          break;
+        }
+      }
+      cg_direction_kernel<<<cg.grid, TPB, 0, st>>>(n, z + o, pv + o, cg.scal, rrho, atol, it == 0 ? 1 : 0);
       GNK_LAUNCH_CHECK(ctx);
       if (int rc = cg.apply(pv, t, 0)) return rc;
       if (int rc = cg.apply(t, q, 1)) return rc;
       if (int rc = gnk_dot(ctx, n, pv + o, q + o, cg.scal + S_PQ, st)) return rc;
       if (int rc = cg.reduce(cg.scal + S_PQ, 1)) return rc;
-      cg_step_kernel<<<cg.grid, TPB, 0, st>>>(n, pv + o, q + o, d_x + o, r + o, cg.scal);
+      cg_step_kernel<<<cg.grid, TPB, 0, st>>>(n, pv + o, q + o, d_x + o, r + o, cg.scal, rrho, atol);
       GNK_LAUNCH_CHECK(ctx);
-      ++*iters;
     }
+    if (pipelined && done_at < 0 && it > 0) {  // ran into maxiter: the test of the last queued iteration has not been looked at yet
+      double rr_last;
+      if (int rc = cg.wait((int)((it - 1) & 1), &rr_last)) return rc;
+      if (sqrt(rr_last) < atol) done_at = it - 1;
+    }
+    *iters += (done_at >= 0) ? done_at : it;
   }
   GNK_CUDA(cudaStreamSynchronize(st));
   return 0;

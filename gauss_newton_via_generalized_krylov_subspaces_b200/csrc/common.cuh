@@ -46,7 +46,11 @@ struct gnk_ctx {
   // gnk_scalars_fetch / gnk_scalars_wait (api.cu): the copy stream and event of the scalar read-back
   cudaStream_t fetch_stream = nullptr;
   cudaEvent_t fetch_event = nullptr;
+  // gnk_cgls (cgls.cu): the stopping test of CG iteration i is read while iteration i + 1 is already queued; two reads in
+  // flight, each with an event on the caller's stream ([0..1]) and one on the copy stream ([2..3])
+  cudaEvent_t cg_event[4] = {nullptr, nullptr, nullptr, nullptr};
 };
+int gnk_ensure_fetch_stream(gnk_ctx* ctx);  // api.cu: creates fetch_stream / fetch_event on first use
 
 constexpr int GNK_PARTIALS = 1 << 19;  // doubles (4 MiB)
 constexpr int GNK_TICKETS = 64;
