@@ -50,8 +50,12 @@ def test_library_holds_the_sm100a_kernels_of_the_hot_path():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     for name in ("cholqr_gram_kernel", "cholqr_gram2_kernel", "cholqr_refine_kernel", "cholqr_factor1_kernel",
                  "cholqr_factor2_kernel", "tsqr_quad_kernel", "apply_kernel", "residual_kernel", "combine_kernel",
-                 "dots_kernel", "update_kernel", "normalize_kernel"):
+                 "dots_kernel", "update_kernel", "normalize_kernel", "normalize_halo_kernel", "stencil_gram_kernel",
+                 "gram_wide_kernel", "gram_pcg_kernel", "wide_factor1_kernel", "wide_refine_kernel",
+                 "wide_factor2_kernel", "cg_precond_kernel", "cg_step_kernel"):
         assert name in sass, name
+    assert "UTMALDG" in sass                       # the TMA-staged row slots of the fused stencil + Gram sweep
+    assert "SYNCS" in sass                         # ... and their mbarriers
     assert sass.count("DMMA.8x8x4") > 500          # Gram passes (and the quad reductions of the Householder leaf)
     assert "LDG.E.EF.128" in sass or "LDG.E.128" in sass
 
