@@ -7,6 +7,7 @@ which does not exist on the GPU box); the fixtures it writes are committed.
     python oracle/gen_golden.py g1025          # Bratu 1024^2 (~5 min)
     python oracle/gen_golden.py g4097          # Bratu 4096^2, 30 iterations (~10 min, 25 GB)
     python oracle/gen_golden.py ttt            # converging grid_resolution=1 runs at 256^2..1024^2 (~4 min)
+    python oracle/gen_golden.py manufactured   # bratu_pde_test.compare_manufactured_solution (~1 min)
 
 Per solver run a fixture stores: the RegressionResult fields, and per callback
 |x|_2, error(x), loss 0.5|res(x)|^2, nfev, cg_iter and x sampled at fixed indices
@@ -245,6 +246,28 @@ def ttt():
         ), y_sample=y[sample_idx(y.shape[0])], u0_sample=u0[sample_idx(u0.shape[0])])
 
 
+def manufactured():
+    """bratu_pde_test.compare_manufactured_solution (:141-190; disabled in the reference's __main__, :337): the right-hand
+    side is the CONTINUOUS operator applied to u = exp(-10 (x1^2 + x2^2)) (sympy, lambdified) instead of the discrete
+    operator applied to u_true, so the solvers converge to the discrete solution u_h and the error curve levels off at
+    the discretisation error.  y is stored in full: it is an input (no sympy needed to replay the run)."""
+    import sympy as sp
+    G, ALPHA, LAMBDA = 101, 5, 10
+    pb = BratuPdeProblem(G, ALPHA, LAMBDA)
+    sx, sy = sp.symbols("sp_x sp_y")
+    su = sp.exp(-10 * (sx**2 + sy**2))
+    sf = -sp.diff(su, sx, sx) - sp.diff(su, sy, sy) + ALPHA * sp.diff(su, sx) + LAMBDA * sp.exp(su)
+    y = sp.lambdify((sx, sy), sf)(*pb.grid).flatten("F")
+    res, jac, err = pb.make_res(y), pb.make_jac(), pb.make_error()
+    np.random.seed(42)
+    u0 = pb.u_true + 0.1 * np.random.normal(loc=0, scale=1, size=len(pb.u_true))
+    save("bratu_g101_manufactured", dict(
+        gn=run(gauss_newton, res, u0, jac, err),
+        gnk_res_old=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100),
+        gnk_res_new=run(gauss_newton_krylow, res, u0, jac, err, max_iter=100, version="res_new"),
+    ), y=y, u0=u0)
+
+
 def cgx0():
     """cg_least_squares with an initial guess (gauss_newton.py:14,46,56 forward x0 to scipy's cg): the Bratu Jacobian at
     grid_nodes=34 and the chained Rosenbrock Jacobian, with and without the discarded unpreconditioned first run."""
@@ -355,4 +378,4 @@ if __name__ == "__main__":
     for what in sys.argv[1:] or ["small"]:
         dict(small=small, g1025=g1025, g4097=g4097, kernels=kernels_fixture, sens101=sens101, sens1025=sens1025,
              sens4097=sens4097, sens4097b=sens4097b, sens1025b=sens1025b, sensd4097=sensd4097, sensd1025=sensd1025, ttt=ttt,
-             cgx0=cgx0)[what]()
+             cgx0=cgx0, manufactured=manufactured)[what]()

@@ -102,6 +102,25 @@ def test_bratu_g101_gauss_newton(g, precond):
         assert abs(a - b) <= max(2, 0.02 * b)
 
 
+def test_bratu_manufactured_solution(g):
+    """bratu_pde_test.compare_manufactured_solution (:141-190): the right-hand side is the continuous
+    operator applied to u (sympy, evaluated by oracle/gen_golden.py from the reference's own expression; y travels in
+    the fixture), so every solver converges to the discrete solution and the error levels off at the discretisation
+    error.  GN and both GNK versions against the reference's traces."""
+    gd = Golden("bratu_g101_manufactured")
+    pb, res, jac, err = _bratu(g, gd, 101)
+    gr = gd.run("gn")
+    rec = Recorder(gr["sample_idx"], err)
+    out = g.gauss_newton(res, gd["u0"], jac, callback=rec)
+    assert (out.nit, out.nrev, out.njev, out.success) == (4, 5, 4, True)
+    assert rel(out.x, gr["x_final"]) < 1e-10 and abs(rec.err[-1] - gr["err"][-1]) < 1e-9 * gr["err"][-1]
+    for a, b in zip(rec.cg, gr["cg_iter"]):
+        assert abs(a - b) <= max(2, 0.02 * b)
+    for rname, kw in (("gnk_res_old", {}), ("gnk_res_new", dict(version="res_new"))):
+        out, rec = _run_gnk(g, res, jac, err, gd["u0"], gd.run(rname), max_iter=100, **kw)
+        assert rec.err[-1] > 0.1 and abs(rec.err[-1] - gd.run(rname)["err"][-1]) < 1e-9 * rec.err[-1]
+
+
 # ------------------------------------------------------------------------------------------------
 # the other Bratu scenarios of bratu_pde_test.py
 # ------------------------------------------------------------------------------------------------

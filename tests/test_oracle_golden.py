@@ -94,6 +94,32 @@ def test_gram_least_squares_variants_follow_the_reference_trajectory(variant):
         assert max(steps) < 1e-10
 
 
+@pytest.mark.parametrize("rname,kw", [("gnk_res_old", {}), ("gnk_res_new", dict(version="res_new"))])
+def test_gnk_bratu_manufactured_solution(rname, kw):
+    """bratu_pde_test.compare_manufactured_solution (:141-190): right-hand side from the continuous operator (sympy in
+    oracle/gen_golden.py: manufactured; y travels in the fixture), all 99 iterations."""
+    gd, o, res, jac, err = _bratu("bratu_g101_manufactured", 101)
+    assert rel(o.start_vector(), gd["u0"]) == 0.0
+    gr = gd.run(rname)
+    rec = Recorder(gr["sample_idx"], err)
+    out = orc.gnk(res, gd["u0"], jac, callback=rec, max_iter=100, **kw)
+    check_trace(rec, gr, 1e-12)
+    assert (out["nit"], out["nfev"], out["njev"], out["success"]) == (
+        int(gr["nit"]), int(gr["nfev"]), int(gr["njev"]), bool(gr["success"])) == (99, 100, 100, False)
+    # the error curve levels off at the discretisation error of the grid, far above the solver tolerance
+    assert np.max(np.abs(np.array(rec.err) / gr["err"] - 1)) < 1e-10 and rec.err[-1] > 0.1
+
+
+def test_gn_bratu_manufactured_solution():
+    gd, o, res, jac, err = _bratu("bratu_g101_manufactured", 101)
+    gr = gd.run("gn")
+    rec = Recorder(gr["sample_idx"], err)
+    out = orc.gn(res, gd["u0"], jac, callback=rec)
+    assert (out["nit"], out["nfev"], out["njev"], out["success"]) == (4, 5, 4, True)
+    assert rel(out["x"], gr["x_final"]) < 1e-10 and abs(rec.err[-1] - gr["err"][-1]) < 1e-9 * gr["err"][-1]
+    assert all(abs(a - b) <= max(2, 0.02 * b) for a, b in zip(rec.cg, gr["cg_iter"]))
+
+
 def test_gn_bratu_g101():
     gd, o, res, jac, err = _bratu("bratu_g101", 101)
     gr = gd.run("gn")
